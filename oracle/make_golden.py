@@ -1,0 +1,218 @@
+"""Generate tests/golden/*.pt by running the REFERENCE's own code (from /root/reference, read-only)
+on seeded synthetic inputs.  Run in the build container only (the GPU box has no /root/reference):
+
+    python oracle/make_golden.py [vit] [ascore] [cscore]
+
+What runs from the reference, unmodified:
+  * llava/model/multimodal_encoder/{clip,dinov2,siglip}_encoder.py — loaded by file path; only the
+    `from_pretrained` entry points (which need network/checkpoints) are replaced by constructors
+    that build the HF model from a config and load our seeded synthetic state dict.
+  * A_score/compute.py — exec'd with only its two hard-coded path/list lines (:7, :10) substituted.
+  * C_score/utils/utils_correspondence.py — imported by file path.
+Inputs are regenerated from seeds by tests (law_of_vision_representation_in_mllms_b200.weights /
+oracle.synth), so fixtures hold only outputs.
+"""
+import importlib.util
+import os
+import sys
+import tempfile
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+REF = "/root/reference"
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+from law_of_vision_representation_in_mllms_b200 import specs as S          # noqa: E402
+from law_of_vision_representation_in_mllms_b200.weights import (           # noqa: E402
+    synthetic_state_dict, synthetic_images)
+from oracle import synth                                                   # noqa: E402
+
+
+def _load(path, name):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+class _Args:
+    def __init__(self, layer=-2, feature="patch"):
+        self.mm_vision_select_layer = layer
+        self.mm_vision_select_feature = feature
+
+
+# ----------------------------------------------------------------------------------- ViT towers
+def _reference_tower(spec, sd, select_layer, select_feature):
+    """Build the reference wrapper for `spec`, with from_pretrained stubbed to (config, sd)."""
+    import transformers as T
+    enc = os.path.join(REF, "llava/model/multimodal_encoder")
+    if spec.family == S.FAMILY_CLIP:
+        mod = _load(os.path.join(enc, "clip_encoder.py"), "ref_clip_encoder")
+        cfg = T.CLIPVisionConfig(hidden_size=spec.hidden_size, intermediate_size=spec.intermediate_size,
+                                 num_hidden_layers=spec.num_layers, num_attention_heads=spec.num_heads,
+                                 image_size=spec.image_size, patch_size=spec.patch_size,
+                                 hidden_act={S.ACT_QUICK_GELU: "quick_gelu", S.ACT_GELU_ERF: "gelu"}[spec.act],
+                                 layer_norm_eps=spec.ln_eps)
+
+        def build(*a, **k):
+            m = T.CLIPVisionModel(cfg)
+            m.load_state_dict(sd, strict=True)
+            return m.eval()
+        mod.CLIPVisionModel = types.SimpleNamespace(from_pretrained=build)
+        mod.CLIPImageProcessor = types.SimpleNamespace(from_pretrained=lambda *a, **k: None)
+        return mod.CLIPVisionTower(spec.name, _Args(select_layer, select_feature))
+    if spec.family == S.FAMILY_DINOV2:
+        mod = _load(os.path.join(enc, "dinov2_encoder.py"), "ref_dinov2_encoder")
+        cfg = T.Dinov2Config(hidden_size=spec.hidden_size, num_hidden_layers=spec.num_layers,
+                             num_attention_heads=spec.num_heads, mlp_ratio=4, image_size=518,
+                             patch_size=spec.patch_size, hidden_act="gelu", layer_norm_eps=spec.ln_eps)
+
+        def build(*a, **k):
+            m = T.Dinov2Model(cfg)
+            m.load_state_dict(sd, strict=True)
+            return m.eval()
+        mod.AutoModel = types.SimpleNamespace(from_pretrained=build)
+        mod.AutoConfig = types.SimpleNamespace(from_pretrained=lambda *a, **k: cfg)
+        mod.AutoImageProcessor = types.SimpleNamespace(from_pretrained=lambda *a, **k: types.SimpleNamespace())
+        return mod.DinoV2VisionTower(spec.name, _Args(select_layer, select_feature))
+    if spec.family == S.FAMILY_SIGLIP:
+        # siglip_encoder.py hard-codes dtype fp16 / device "cuda" (:59-64) and under transformers 5.5
+        # `.vision_model(..., output_hidden_states=True).hidden_states` is None, so the
+        # wrapper cannot run on CPU.  Drive HF SiglipVisionModel directly and apply the wrapper's
+        # feature_select (:30-38) with its hard-coded 'cls_patch'.
+        cfg = T.SiglipVisionConfig(hidden_size=spec.hidden_size, intermediate_size=spec.intermediate_size,
+                                   num_hidden_layers=spec.num_layers, num_attention_heads=spec.num_heads,
+                                   image_size=spec.image_size, patch_size=spec.patch_size,
+                                   hidden_act="gelu_pytorch_tanh", layer_norm_eps=spec.ln_eps)
+        m = T.SiglipVisionModel(cfg)
+        missing = m.load_state_dict(sd, strict=False)
+        assert all(k.startswith("vision_model.head.") for k in missing.missing_keys), missing
+        m.eval()
+
+        class _Sig(torch.nn.Module):
+            def forward(self, images):
+                hs = m(images.float(), output_hidden_states=True).hidden_states
+                return hs[select_layer].to(images.dtype)
+        return _Sig()
+    raise ValueError(spec.family)
+
+
+VIT_CASES = [
+    # name, tower key, layers kept (None = full depth), image size, n images, select_layer, select_feature
+    ("clip224_full", "openai/clip-vit-large-patch14", None, 224, 2, -2, "patch"),
+    ("clip336_full", "openai/clip-vit-large-patch14-336", None, 336, 1, -2, "patch"),
+    ("clip336_l3", "openai/clip-vit-large-patch14-336", 3, 336, 2, -2, "patch"),
+    ("clip224_l3_clspatch", "openai/clip-vit-large-patch14", 3, 224, 2, -1, "cls_patch"),
+    ("openclip224_l3", "laion/CLIP-ViT-L-14-laion2B-s32B-b82K", 3, 224, 2, -2, "patch"),
+    ("dinov2_224_l3", "facebook/dinov2-large", 3, 224, 2, -2, "patch"),
+    ("dinov2_336_l3", "facebook/dinov2-large", 3, 336, 2, -2, "patch"),
+    ("dinov2_336_full", "facebook/dinov2-large", None, 336, 1, -2, "patch"),
+    ("siglip224_l3", "google/siglip-base-patch16-224", 3, 224, 2, -2, "cls_patch"),
+    ("siglip224_full", "google/siglip-base-patch16-224", None, 224, 2, -2, "cls_patch"),
+]
+VIT_TOKENS = 12   # token rows kept per image
+
+
+def vit_case_inputs(case):
+    name, key, nl, size, n, sl, sf = case
+    spec = S.TOWER_SPECS[key]
+    if nl is not None:
+        spec = S.tiny_spec(spec, nl)
+    seed = 100 + sum(map(ord, name)) % 1000
+    sd = synthetic_state_dict(spec, seed=seed)
+    imgs = synthetic_images(n, size, seed=seed + 1)
+    return spec, sd, imgs
+
+
+def token_rows(T):
+    g = torch.Generator().manual_seed(T)
+    rows = torch.randperm(T, generator=g)[:VIT_TOKENS - 2].tolist()
+    return sorted(set(rows + [0, T - 1]))
+
+
+def make_vit():
+    for case in VIT_CASES:
+        name, key, nl, size, n, sl, sf = case
+        spec, sd, imgs = vit_case_inputs(case)
+        tower = _reference_tower(spec, sd, sl, sf)
+        with torch.no_grad():
+            out = tower(imgs)                       # [N,P,D] fp32
+            out_list = None
+            if name == "clip336_l3":                # the list-of-3D-tensors calling convention
+                out_list = tower([im for im in imgs])
+        rows = token_rows(out.shape[1])
+        rec = dict(case=case, shape=tuple(out.shape), rows=rows, values=out[:, rows].clone(),
+                   fro=out.flatten(1).norm(dim=1), mean=out.flatten(1).mean(dim=1),
+                   abs_mean=out.abs().flatten(1).mean(dim=1))
+        if out_list is not None:
+            rec["list_equal_batch"] = bool(all(torch.allclose(o[0], out[i], atol=1e-5) for i, o in enumerate(out_list)))
+            rec["list_shapes"] = [tuple(o.shape) for o in out_list]
+        torch.save(rec, os.path.join(GOLD, f"vit_{name}.pt"))
+        print("vit", name, tuple(out.shape), "fro", rec["fro"].tolist())
+
+
+# ----------------------------------------------------------------------------------- A score
+def make_ascore():
+    src = open(os.path.join(REF, "A_score/compute.py")).read()
+    out = {}
+    for cname, cfg in synth.A_SCORE_CASES.items():
+        with tempfile.TemporaryDirectory() as tmp:
+            feats = synth.a_score_features(cfg)
+            for sub, tensors in feats.items():
+                os.makedirs(os.path.join(tmp, sub))
+                for i, t in enumerate(tensors):
+                    torch.save(t, os.path.join(tmp, sub, f"tensor_{i + 1}.pt"))
+            res = {}
+            for sub in feats:                       # one exec per subfolder to read the per-image lists
+                s = src.replace("base_folder = '/any/path/mmbench'", f"base_folder = {tmp!r}")
+                s = s.replace("subfolders = ['clip336', 'clip224', 'dino', 'dit', 'imsd', 'openclip', 'sd1.5', "
+                              "'sd2.1', 'sd3', 'sdxl']", f"subfolders = [{sub!r}]")
+                assert s != src
+                ns = {"__name__": "ref_a_score"}
+                exec(compile(s, "A_score/compute.py", "exec"), ns)
+                res[sub] = dict(result=ns["results"][sub], per_image_336=list(ns["cosine_similarities_336"]),
+                                per_image_224=list(ns["cosine_similarities_224"]))
+                print("ascore", cname, sub, res[sub]["result"])
+            out[cname] = res
+    torch.save(out, os.path.join(GOLD, "a_score.pt"))
+
+
+# ----------------------------------------------------------------------------------- C score
+def make_cscore():
+    uc = _load(os.path.join(REF, "C_score/utils/utils_correspondence.py"), "ref_utils_correspondence")
+    out = {}
+    for cname, cfg in synth.C_SCORE_CASES.items():
+        d1, d2, kps = synth.c_score_pair(cfg)
+        P = cfg["P"]
+        # normalize_feats restated from C_score/pck_train.py:24-29 (module not importable offline)
+        nf = lambda f: f / (torch.linalg.norm(f, dim=-1)[:, :, None] + 1e-10)
+        d1n, d2n = nf(d1), nf(d2)
+        rec = {}
+        for soft in (True, False):
+            args = types.SimpleNamespace(ANNO_SIZE=840, SOFT_EVAL=soft, SOFT_EVAL_WINDOW=cfg["window"])
+            idx = uc.kpts_to_patch_idx(args, kps, P)
+            k12 = uc.calculate_keypoint_transformation(args, d1n, d2n, torch.as_tensor(idx, dtype=torch.long), P)
+            rec["soft" if soft else "hard"] = k12.clone()
+            rec["patch_idx"] = torch.as_tensor(idx)
+        sim = torch.matmul(d1n, d2n.permute(0, 2, 1))[0]
+        rec["flow"] = uc.get_flow(sim, cfg["window"], P).reshape(-1, 2).clone()
+        rec["argmax"] = sim.argmax(dim=-1)
+        out[cname] = rec
+        print("cscore", cname, rec["soft"][:2].tolist())
+    torch.save(out, os.path.join(GOLD, "c_score.pt"))
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLD, exist_ok=True)
+    what = sys.argv[1:] or ["vit", "ascore", "cscore"]
+    torch.set_num_threads(os.cpu_count())
+    if "ascore" in what:
+        make_ascore()
+    if "cscore" in what:
+        make_cscore()
+    if "vit" in what:
+        make_vit()
