@@ -1,0 +1,130 @@
+/* lovr_b200 — C ABI of the B200-native vision-representation scoring path.
+ *
+ * The reference (bronyayang/Law_of_Vision_Representation_in_MLLMs) has NO native/FFI boundary on this path
+ * (SURVEY.md §0 F5): its "operator API" is the Python nn.Module contract of the tower classes plus two
+ * score scripts.  This header is the boundary a native replacement needs; every entry point cites the
+ * reference interface it stands behind.  The Python mirror of the reference classes
+ * (law_of_vision_representation_in_mllms_b200/towers.py etc.) binds these symbols with ctypes.
+ *
+ * Conventions: plain pointers and sizes only; all pointers are DEVICE pointers unless named *_host;
+ * the caller owns every buffer (the library never allocates or frees caller memory; its only internal
+ * allocations are small host-side plan objects); all work is enqueued on `stream` (a CUstream /
+ * cudaStream_t handle passed as void*) with no host synchronisation; return 0 on success, a negative
+ * LOVR_E_* code on failure with a message available from lovr_last_error() (thread-local).
+ * There is no CPU fallback: without an sm_100 device every compute entry point fails.
+ */
+#ifndef LOVR_B200_H_
+#define LOVR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LOVR_ABI_VERSION 1
+
+enum { LOVR_OK = 0, LOVR_E_ARG = -1, LOVR_E_CUDA = -2, LOVR_E_UNSUPPORTED = -3, LOVR_E_NOMEM = -4 };
+enum { LOVR_DT_F32 = 0, LOVR_DT_BF16 = 1, LOVR_DT_F16 = 2 };
+/* hidden_act of the HF config: quick_gelu (openai CLIP), gelu (OpenCLIP, DINOv2), gelu_pytorch_tanh (SigLIP) */
+enum { LOVR_ACT_NONE = 0, LOVR_ACT_QUICK_GELU = 1, LOVR_ACT_GELU_ERF = 2, LOVR_ACT_GELU_TANH = 3 };
+enum { LOVR_EPI_BF16 = 0, LOVR_EPI_RESID_F32 = 1, LOVR_EPI_F32 = 2 };
+enum { LOVR_ATTN_TCGEN05 = 0, LOVR_ATTN_SIMT_CHECK = 1 };
+
+int lovr_abi_version(void);
+const char* lovr_last_error(void);
+/* number of kernels this library has launched on the calling thread since load (bench.py's gpu_launches) */
+uint64_t lovr_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Vision tower (replaces the arithmetic behind CLIPVisionTower.forward / DinoV2VisionTower.forward /
+ * SigLipVisionTower.forward: llava/model/multimodal_encoder/clip_encoder.py:39-51,
+ * dinov2_encoder.py:32-54, siglip_encoder.py:30-52, i.e. HF CLIPVisionModel / Dinov2Model /
+ * SiglipVisionModel with output_hidden_states=True followed by feature_select).
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t hidden_size;       /* 1024 | 768 (multiple of 128) */
+  int32_t intermediate_size; /* 4096 | 3072 */
+  int32_t num_layers;        /* layers present in the weights */
+  int32_t num_heads;         /* head_dim must be 64 */
+  int32_t image_size;        /* input resolution this instance runs at */
+  int32_t patch_size;
+  int32_t act;               /* LOVR_ACT_* */
+  int32_t has_cls;
+  int32_t pre_ln;            /* CLIP pre_layrnorm */
+  int32_t layerscale;        /* DINOv2 LayerScale */
+  float ln_eps;
+  int32_t patch_k_padded;    /* 3*patch*patch rounded up to a multiple of 64 (im2col K) */
+} lovr_tower_config;
+
+typedef struct {
+  const float* ln1_w; const float* ln1_b;
+  const void* qkv_w;  /* bf16 [3D, D] rows = q,k,v output features */
+  const float* qkv_b; /* [3D] */
+  const void* o_w;    /* bf16 [D, D] */
+  const float* o_b;
+  const float* ls1;   /* [D] or NULL */
+  const float* ln2_w; const float* ln2_b;
+  const void* fc1_w;  /* bf16 [I, D] */
+  const float* fc1_b;
+  const void* fc2_w;  /* bf16 [D, I] */
+  const float* fc2_b;
+  const float* ls2;   /* [D] or NULL */
+} lovr_layer_weights;
+
+typedef struct {
+  const void* patch_w;   /* bf16 [D, patch_k_padded], k = c*P*P + py*P + px, zero padded */
+  const float* patch_b;  /* [D] or NULL (CLIP has no conv bias) */
+  const float* cls;      /* [D] or NULL */
+  const float* pos;      /* [T, D] (already interpolated for image_size: DINOv2) */
+  const float* pre_ln_w; const float* pre_ln_b; /* or NULL */
+  const lovr_layer_weights* layers_host; /* HOST array [num_layers] of device pointers */
+} lovr_tower_weights;
+
+typedef struct lovr_tower lovr_tower_t;
+
+/* bytes of device workspace needed to run up to max_batch images per forward call */
+size_t lovr_tower_workspace_bytes(const lovr_tower_config* cfg, int32_t max_batch);
+int lovr_tower_create(lovr_tower_t** out, const lovr_tower_config* cfg, const lovr_tower_weights* w,
+                      void* workspace, size_t workspace_bytes, int32_t max_batch);
+void lovr_tower_destroy(lovr_tower_t* t);
+/* pixels [n,3,R,R] in pixel_dtype (NCHW, already normalised like the HF processors do) ->
+ * out[n, p, out_col_off : out_col_off + D], row stride out_ld elements, dtype out_dtype.
+ * layers_to_run = select_layer mod (L+1) (hidden_states[select_layer]); drop_cls=1 for 'patch'.
+ * attn_impl: LOVR_ATTN_TCGEN05 (product) or LOVR_ATTN_SIMT_CHECK (cross-check kernel for tests). */
+int lovr_tower_forward(lovr_tower_t* t, const void* pixels, int32_t pixel_dtype, int32_t n_img,
+                       int32_t layers_to_run, int32_t drop_first_token, void* out, int32_t out_dtype,
+                       int64_t out_ld, int64_t out_col_off, int32_t attn_impl, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Building blocks (exported so each kernel is parity-tested in isolation through the same ABI).
+ * ------------------------------------------------------------------------------------------------- */
+/* C[M,N] = epilogue(A[M,K] bf16 · W[N,K]^T bf16): nn.Linear semantics. lda/ldw/ldc in elements.
+ * LOVR_EPI_BF16: C bf16 = act(acc+bias). LOVR_EPI_F32: C fp32 = acc+bias.
+ * LOVR_EPI_RESID_F32: C fp32 += colscale*(acc+bias) in place. */
+int lovr_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int32_t M,
+                   int32_t N, int32_t K, int32_t epi, int32_t act, const float* bias, const float* colscale,
+                   void* stream);
+int lovr_layernorm_bf16(const float* x, const float* gamma, const float* beta, float eps, void* y_bf16,
+                        int64_t rows, int32_t D, void* stream);
+/* qkv bf16 [n_img*T, 3*H*64] -> out bf16 [n_img*T, H*64]; softmax(q k^T / 8) v per (image, head) */
+int lovr_attention(const void* qkv, void* out, int32_t n_img, int32_t T, int32_t H, int32_t impl, void* stream);
+int lovr_im2col(const void* pixels, int32_t pixel_dtype, void* cols_bf16, int32_t n_img, int32_t image_size,
+                int32_t patch, int32_t k_padded, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * A score (replaces the per-pair arithmetic of A_score/compute.py:54-72):
+ *   pair_score[b] = mean_i max_j cos(n(other[b,i,:]), n(ref[b,j,:])),  n(x)=x/(||x||+1e-10), cos eps 1e-8.
+ * other [n_pairs, x, D], ref [n_pairs, y, D] contiguous, dtype bf16 (exact products, fp32 accumulate) or
+ * fp32 (split into bf16 hi/lo terms on the fly, |error| ~1e-6).  The 100-image and (336,224) averaging of
+ * compute.py:75-81 is host arithmetic on pair_score (see a_score.py).
+ * ------------------------------------------------------------------------------------------------- */
+size_t lovr_a_score_workspace_bytes(int32_t dtype, int64_t n_pairs, int32_t x, int32_t y, int32_t D);
+int lovr_a_score_maxcos(const void* other, const void* ref, int32_t dtype, int64_t n_pairs, int32_t x, int32_t y,
+                        int32_t D, float* pair_score, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LOVR_B200_H_ */

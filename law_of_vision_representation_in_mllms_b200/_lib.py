@@ -1,0 +1,111 @@
+"""ctypes binding of liblovr_b200.so (the C ABI in include/lovr_b200.h).
+
+The shared library is built in-tree by `build.py` (nvcc, sm_100a).  There is no fallback: if the
+library is missing or a call fails, the Python layer raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblovr_b200.so")
+
+OK, E_ARG, E_CUDA, E_UNSUPPORTED, E_NOMEM = 0, -1, -2, -3, -4
+DT_F32, DT_BF16, DT_F16 = 0, 1, 2
+EPI_BF16, EPI_RESID_F32, EPI_F32 = 0, 1, 2
+ATTN_TCGEN05, ATTN_SIMT_CHECK = 0, 1
+
+# every symbol include/lovr_b200.h declares (tests/test_abi.py checks the library exports all of them)
+EXPORTS = [
+    "lovr_abi_version", "lovr_last_error", "lovr_launch_count",
+    "lovr_tower_workspace_bytes", "lovr_tower_create", "lovr_tower_destroy", "lovr_tower_forward",
+    "lovr_gemm_bf16", "lovr_layernorm_bf16", "lovr_attention", "lovr_im2col",
+    "lovr_a_score_workspace_bytes", "lovr_a_score_maxcos",
+]
+
+
+class TowerConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("hidden_size", "intermediate_size", "num_layers", "num_heads", "image_size",
+                                         "patch_size", "act", "has_cls", "pre_ln", "layerscale")] + \
+               [("ln_eps", C.c_float), ("patch_k_padded", C.c_int32)]
+
+
+class LayerWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("ln1_w", "ln1_b", "qkv_w", "qkv_b", "o_w", "o_b", "ls1", "ln2_w", "ln2_b",
+                                          "fc1_w", "fc1_b", "fc2_w", "fc2_b", "ls2")]
+
+
+class TowerWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("patch_w", "patch_b", "cls", "pos", "pre_ln_w", "pre_ln_b")] + \
+               [("layers_host", C.POINTER(LayerWeights))]
+
+
+class LovrError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load the shared library once; raise loudly if it is absent (no CPU fallback exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LovrError(
+            f"{LIB_PATH} not found: build it with `python -m law_of_vision_representation_in_mllms_b200.build` "
+            "(nvcc, sm_100a). This package has no CPU or PyTorch fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, f32, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
+    L.lovr_abi_version.restype = C.c_int
+    L.lovr_last_error.restype = C.c_char_p
+    L.lovr_launch_count.restype = C.c_uint64
+    L.lovr_tower_workspace_bytes.restype = sz
+    L.lovr_tower_workspace_bytes.argtypes = [C.POINTER(TowerConfig), i32]
+    L.lovr_tower_create.restype = C.c_int
+    L.lovr_tower_create.argtypes = [C.POINTER(vp), C.POINTER(TowerConfig), C.POINTER(TowerWeights), vp, sz, i32]
+    L.lovr_tower_destroy.restype = None
+    L.lovr_tower_destroy.argtypes = [vp]
+    L.lovr_tower_forward.restype = C.c_int
+    L.lovr_tower_forward.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32, i64, i64, i32, vp]
+    L.lovr_gemm_bf16.restype = C.c_int
+    L.lovr_gemm_bf16.argtypes = [vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, i32, vp, vp, vp]
+    L.lovr_layernorm_bf16.restype = C.c_int
+    L.lovr_layernorm_bf16.argtypes = [vp, vp, vp, f32, vp, i64, i32, vp]
+    L.lovr_attention.restype = C.c_int
+    L.lovr_attention.argtypes = [vp, vp, i32, i32, i32, i32, vp]
+    L.lovr_im2col.restype = C.c_int
+    L.lovr_im2col.argtypes = [vp, i32, vp, i32, i32, i32, i32, vp]
+    L.lovr_a_score_workspace_bytes.restype = sz
+    L.lovr_a_score_workspace_bytes.argtypes = [i32, i64, i32, i32, i32]
+    L.lovr_a_score_maxcos.restype = C.c_int
+    L.lovr_a_score_maxcos.argtypes = [vp, vp, i32, i64, i32, i32, i32, vp, vp, sz, vp]
+    _lib = L
+    return L
+
+
+def check(rc, what=""):
+    if rc != OK:
+        msg = lib().lovr_last_error().decode("utf-8", "replace")
+        raise LovrError(f"{what or 'lovr call'} failed ({rc}): {msg}")
+
+
+def launch_count():
+    return int(lib().lovr_launch_count())
+
+
+def torch_dtype_code(dtype):
+    import torch
+    try:
+        return {torch.float32: DT_F32, torch.bfloat16: DT_BF16, torch.float16: DT_F16}[dtype]
+    except KeyError:
+        raise LovrError(f"unsupported dtype {dtype}: the device path takes float32, bfloat16 or float16") from None
+
+
+def stream_ptr(device=None):
+    import torch
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)

@@ -1,0 +1,365 @@
+// Persistent warp-specialised tcgen05 GEMM for sm_100a:  C[M,N] = epilogue(A[M,K] · W[N,K]^T)
+//
+//   warp 0 (1 thread)  TMA producer: A tile 128x64 and W tile BNx64 (bf16, K-major, 128-B swizzle)
+//                      into a kStages-deep smem ring, completion on `full` mbarriers.
+//   warp 1 (1 thread)  MMA issuer: tcgen05.mma cta_group::1 kind::f16, 128 x BN x 16 per instruction,
+//                      fp32 accumulator in TMEM, double-buffered (2 x BN columns); tcgen05.commit
+//                      releases smem stages (`empty`) and publishes accumulators (`tmem_full`).
+//   warps 2..5         epilogue: tcgen05.ld (thread = accumulator row), fused bias / activation /
+//                      LayerScale / residual / row-max, 128-B-swizzled smem staging, TMA store.
+//
+// Tiles are visited unit-major: unit = (batch, m_tile, n_group); each unit runs `n_inner` consecutive
+// n tiles (n_inner = 1 for the dense layers; = all n tiles for the row-max epilogue so the running
+// maximum stays in registers).  Rows beyond M are zero-filled by TMA on load and clipped on store.
+#pragma once
+#include "ptx.cuh"
+
+namespace lovr {
+
+enum : int { ACT_NONE = 0, ACT_QUICK_GELU = 1, ACT_GELU_ERF = 2, ACT_GELU_TANH = 3 };
+enum : int {
+  EPI_BF16 = 0,      // C bf16  = act(acc + bias)
+  EPI_RESID_F32 = 1, // C fp32 += colscale * (acc + bias)          (in place residual stream)
+  EPI_F32 = 2,       // C fp32  = acc + bias
+  EPI_ROWMAX = 3     // rowmax[b,row] = rowscale[b,row] * max_col(acc * colscale[b,col]), cols < n_valid
+};
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kStages = 4;
+constexpr int kEpiWarps = 4;
+constexpr int kGemmThreads = 64 + kEpiWarps * 32;
+constexpr int kStageBufBytes = 32 * 128;  // one epilogue staging box: 32 rows x 128 B
+
+struct GemmArgs {
+  int M;            // rows of A per batch entry
+  int N;            // columns of C (= rows of W) per batch entry, multiple of BN unless EPI_ROWMAX
+  int K;            // multiple of 64
+  int batch;        // >= 1; >1 uses the 3rd tensor-map coordinate
+  int n_inner;      // n tiles per unit
+  const float* bias;      // [N] or nullptr
+  const float* colscale;  // EPI_RESID_F32: [N] LayerScale or nullptr;  EPI_ROWMAX: [batch, N] 1/||ref||
+  const float* rowscale;  // EPI_ROWMAX: [batch, M] 1/||other||
+  float* rowmax;          // EPI_ROWMAX: [batch, M]
+  int n_valid;            // EPI_ROWMAX: real number of columns (<= N)
+};
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStagingBytes = kEpiWarps * 2 * kStageBufBytes;
+  static constexpr int kBarBytes = 256;
+  static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + kBarBytes + 1024 /*align slack*/;
+};
+
+template <int act>
+__device__ __forceinline__ float apply_act(float x) {
+  if constexpr (act == ACT_QUICK_GELU) {
+    // x * sigmoid(1.702 x)
+    return __fdividef(x, 1.0f + __expf(-1.702f * x));
+  } else if constexpr (act == ACT_GELU_ERF) {
+    return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+  } else if constexpr (act == ACT_GELU_TANH) {
+    const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+    // tanh(u) = 1 - 2/(exp(2u)+1)
+    const float t = 1.0f - __fdividef(2.0f, __expf(2.0f * u) + 1.0f);
+    return 0.5f * x * (1.0f + t);
+  }
+  return x;
+}
+
+template <int BN, int EPI, int ACT>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmC, const GemmArgs p) {
+  using L = GemmSmem<BN>;
+  static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N constraint for M=128");
+  constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  constexpr uint32_t kIdesc = make_idesc_bf16(kBM, BN, 0, 0);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stage_base = smem;
+  uint8_t* staging = smem + kStages * L::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + L::kStagingBytes);
+  uint64_t* full_bar = bars;                    // [kStages]
+  uint64_t* empty_bar = bars + kStages;         // [kStages]
+  uint64_t* tmem_full = bars + 2 * kStages;     // [2]
+  uint64_t* tmem_empty = bars + 2 * kStages + 2;  // [2]
+  uint64_t* resid_bar = bars + 2 * kStages + 4;   // [kEpiWarps][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4 + 2 * kEpiWarps);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_tiles = (p.M + kBM - 1) / kBM;
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const int n_groups = n_tiles / p.n_inner;
+  const int units = p.batch * m_tiles * n_groups;
+  const int k_blocks = p.K / kBK;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (EPI != EPI_ROWMAX) tma_prefetch_desc(&tmC);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], kEpiWarps);
+    }
+    for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&resid_bar[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+        const int ng = unit % n_groups;
+        const int mt = (unit / n_groups) % m_tiles;
+        const int b = unit / (n_groups * m_tiles);
+        for (int ni = 0; ni < p.n_inner; ++ni) {
+          const int nt = ng * p.n_inner + ni;
+          for (int kb = 0; kb < k_blocks; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = stage_base + stage * L::kStageBytes;
+            uint8_t* sb = sa + L::kABytes;
+            mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+            tma_load_3d(sa, &tmA, &full_bar[stage], kb * kBK, mt * kBM, b);
+            tma_load_3d(sb, &tmB, &full_bar[stage], kb * kBK, nt * BN, b);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+        for (int ni = 0; ni < p.n_inner; ++ni) {
+          mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * BN;
+          for (int kb = 0; kb < k_blocks; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(stage_base + stage * L::kStageBytes);
+            const uint32_t sb = sa + L::kABytes;
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k) {
+              const uint64_t adesc = make_smem_desc_sw128(sa + k * 32, 16, 1024);
+              const uint64_t bdesc = make_smem_desc_sw128(sb + k * 32, 16, 1024);
+              umma_bf16_ss(d_tmem, adesc, bdesc, kIdesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);  // smem stage reusable once these MMAs retire
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(&tmem_full[acc]);
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===================================================================== epilogue warps
+    const int ew = warp - 2;       // staging / barrier slot
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    uint8_t* my_stage = staging + ew * 2 * kStageBufBytes;
+    uint64_t* my_rbar = resid_bar + ew * 2;
+    const uint32_t row_sw = (lane & 7);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint32_t g = 0;  // running chunk counter -> staging buffer / barrier parity
+    for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+      const int ng = unit % n_groups;
+      const int mt = (unit / n_groups) % m_tiles;
+      const int b = unit / (n_groups * m_tiles);
+      const int row0 = mt * kBM + quarter * 32;
+      float run_max = -INFINITY;
+      for (int ni = 0; ni < p.n_inner; ++ni) {
+        const int nt = ng * p.n_inner + ni;
+        const int col_tile = nt * BN;
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+
+        if constexpr (EPI == EPI_BF16) {
+          constexpr int CH = 64;
+#pragma unroll 1
+          for (int c = 0; c < BN / CH; ++c, ++g) {
+            uint32_t r0[32], r1[32];
+            tmem_ld_32x32b_x32(t_row + c * CH, r0);
+            tmem_ld_32x32b_x32(t_row + c * CH + 32, r1);
+            uint8_t* buf = my_stage + (g & 1) * kStageBufBytes;
+            if (lane == 0) tma_store_wait_read<1>();  // the store issued 2 chunks ago has drained this buffer
+            __syncwarp();
+            tmem_ld_wait();
+            const int col0 = col_tile + c * CH;
+            const uint32_t buf_row = smem_u32(buf) + lane * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float v[8];
+              float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+              if (p.bias) {
+                b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j * 8));
+                b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j * 8 + 4));
+              }
+              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int cc = j * 8 + e;
+                const float x = __uint_as_float(cc < 32 ? r0[cc] : r1[cc - 32]) + bb[e];
+                v[e] = apply_act<ACT>(x);
+              }
+              st_shared_v4(buf_row + ((j ^ row_sw) << 4), pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                           pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(&tmC, buf, col0, row0, b);
+              tma_store_commit();
+            }
+          }
+        } else if constexpr (EPI == EPI_F32) {
+          constexpr int CH = 32;
+#pragma unroll 1
+          for (int c = 0; c < BN / CH; ++c, ++g) {
+            uint32_t r0[32];
+            tmem_ld_32x32b_x32(t_row + c * CH, r0);
+            uint8_t* buf = my_stage + (g & 1) * kStageBufBytes;
+            if (lane == 0) tma_store_wait_read<1>();
+            __syncwarp();
+            tmem_ld_wait();
+            const int col0 = col_tile + c * CH;
+            const uint32_t buf_row = smem_u32(buf) + lane * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float v[4];
+              float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.bias) b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j * 4));
+              const float bb[4] = {b0.x, b0.y, b0.z, b0.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) v[e] = __uint_as_float(r0[j * 4 + e]) + bb[e];
+              st_shared_v4(buf_row + ((j ^ row_sw) << 4), __float_as_uint(v[0]), __float_as_uint(v[1]),
+                           __float_as_uint(v[2]), __float_as_uint(v[3]));
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(&tmC, buf, col0, row0, b);
+              tma_store_commit();
+            }
+          }
+        } else if constexpr (EPI == EPI_RESID_F32) {
+          constexpr int CH = 32;
+          constexpr int NCH = BN / CH;
+          // prefetch residual chunk 0 of this tile
+          if (lane == 0) {
+            tma_store_wait_read<0>();
+            uint8_t* buf = my_stage + (g & 1) * kStageBufBytes;
+            mbar_arrive_expect_tx(&my_rbar[g & 1], kStageBufBytes);
+            tma_load_3d(buf, &tmC, &my_rbar[g & 1], col_tile, row0, b);
+          }
+#pragma unroll 1
+          for (int c = 0; c < NCH; ++c, ++g) {
+            uint32_t r0[32];
+            tmem_ld_32x32b_x32(t_row + c * CH, r0);
+            if (lane == 0 && c + 1 < NCH) {
+              // buffer (g+1)&1 was last read by the store of chunk g-1
+              tma_store_wait_read<0>();
+              uint8_t* nbuf = my_stage + ((g + 1) & 1) * kStageBufBytes;
+              mbar_arrive_expect_tx(&my_rbar[(g + 1) & 1], kStageBufBytes);
+              tma_load_3d(nbuf, &tmC, &my_rbar[(g + 1) & 1], col_tile + (c + 1) * CH, row0, b);
+            }
+            uint8_t* buf = my_stage + (g & 1) * kStageBufBytes;
+            mbar_wait(&my_rbar[g & 1], (g >> 1) & 1);
+            tmem_ld_wait();
+            const int col0 = col_tile + c * CH;
+            const uint32_t buf_row = smem_u32(buf) + lane * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              uint32_t q0, q1, q2, q3;
+              const uint32_t addr = buf_row + ((j ^ row_sw) << 4);
+              ld_shared_v4(addr, q0, q1, q2, q3);
+              float res[4] = {__uint_as_float(q0), __uint_as_float(q1), __uint_as_float(q2), __uint_as_float(q3)};
+              float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), s0 = make_float4(1.f, 1.f, 1.f, 1.f);
+              if (p.bias) b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j * 4));
+              if (p.colscale) s0 = __ldg(reinterpret_cast<const float4*>(p.colscale + col0 + j * 4));
+              const float bb[4] = {b0.x, b0.y, b0.z, b0.w};
+              const float ss[4] = {s0.x, s0.y, s0.z, s0.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) res[e] += (__uint_as_float(r0[j * 4 + e]) + bb[e]) * ss[e];
+              st_shared_v4(addr, __float_as_uint(res[0]), __float_as_uint(res[1]), __float_as_uint(res[2]),
+                           __float_as_uint(res[3]));
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(&tmC, buf, col0, row0, b);
+              tma_store_commit();
+            }
+          }
+        } else {  // EPI_ROWMAX
+          constexpr int CH = 32;
+          const float* cs = p.colscale + static_cast<size_t>(b) * p.N;
+#pragma unroll 1
+          for (int c = 0; c < BN / CH; ++c) {
+            const int col0 = col_tile + c * CH;
+            if (col0 >= p.n_valid) break;  // warp-uniform
+            uint32_t r0[32];
+            tmem_ld_32x32b_x32(t_row + c * CH, r0);
+            tmem_ld_wait();
+#pragma unroll
+            for (int cc = 0; cc < 32; ++cc) {
+              const float x = __uint_as_float(r0[cc]) * __ldg(cs + min(col0 + cc, p.N - 1));
+              if (col0 + cc < p.n_valid) run_max = fmaxf(run_max, x);
+            }
+          }
+        }
+        // all TMEM reads of this accumulator are complete (tcgen05.wait::ld above)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+      if constexpr (EPI == EPI_ROWMAX) {
+        const int row = row0 + lane;
+        if (row < p.M) {
+          const size_t idx = static_cast<size_t>(b) * p.M + row;
+          p.rowmax[idx] = run_max * __ldg(p.rowscale + idx);
+        }
+      }
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace lovr

@@ -1,0 +1,543 @@
+// Host side of liblovr_b200.so: tensor-map construction, kernel launchers, the tower forward schedule
+// and the extern "C" entry points declared in include/lovr_b200.h.  No torch types, no CPU fallback.
+#include "../../include/lovr_b200.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "attention.cuh"
+#include "attention_simt.cuh"
+#include "gemm.cuh"
+#include "rowwise.cuh"
+#include "scores.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+thread_local uint64_t g_launches = 0;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t e_ = (expr);                                                                \
+    if (e_ != cudaSuccess) return fail(LOVR_E_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+  } while (0)
+
+#define LAUNCH_CHECK(name)                                                                         \
+  do {                                                                                             \
+    ++g_launches;                                                                                  \
+    cudaError_t e_ = cudaGetLastError();                                                           \
+    if (e_ != cudaSuccess) return fail(LOVR_E_CUDA, "launch %s: %s", name, cudaGetErrorString(e_)); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------ device info
+struct DeviceInfo {
+  int sms = 0;
+  int cc_major = 0;
+  bool ok = false;
+  std::string why;
+};
+const DeviceInfo& device_info() {
+  static DeviceInfo info = [] {
+    DeviceInfo d;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+      d.why = std::string("no CUDA device: ") + cudaGetErrorString(e);
+      return d;
+    }
+    cudaDeviceProp p;
+    e = cudaGetDeviceProperties(&p, dev);
+    if (e != cudaSuccess) {
+      d.why = cudaGetErrorString(e);
+      return d;
+    }
+    d.sms = p.multiProcessorCount;
+    d.cc_major = p.major;
+    if (p.major != 10) {
+      d.why = "lovr_b200 kernels are sm_100a-only (tcgen05/TMEM); device is sm_" + std::to_string(p.major) +
+              std::to_string(p.minor);
+      return d;
+    }
+    d.ok = true;
+    return d;
+  }();
+  return info;
+}
+int require_device() {
+  const DeviceInfo& d = device_info();
+  if (!d.ok) return fail(LOVR_E_UNSUPPORTED, "%s", d.why.c_str());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ tensor maps
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// 3-D row-major tensor {dim0 (contiguous), dim1, dim2}; strides in elements; 128-byte swizzle;
+// box {box0, box1, 1}; out-of-bounds reads return zero, out-of-bounds writes are dropped.
+int make_tmap(CUtensorMap* m, const void* ptr, int elem_bytes, uint64_t dim0, uint64_t dim1, uint64_t dim2,
+              uint64_t stride1_elems, uint64_t stride2_elems, uint32_t box0, uint32_t box1) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(LOVR_E_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  if (box0 * elem_bytes != 128) return fail(LOVR_E_ARG, "tensor-map inner box must span 128 bytes");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (stride1_elems * elem_bytes) % 16 || (stride2_elems * elem_bytes) % 16)
+    return fail(LOVR_E_ARG, "tensor-map base/strides must be 16-byte aligned");
+  const CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  cuuint64_t dims[3] = {dim0, dim1, dim2};
+  cuuint64_t strides[2] = {stride1_elems * elem_bytes, stride2_elems * elem_bytes};
+  cuuint32_t box[3] = {box0, box1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, dt, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(LOVR_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ GEMM launch
+template <int BN, int EPI, int ACT>
+int launch_gemm_inst(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const lovr::GemmArgs& args,
+                     cudaStream_t s) {
+  auto kern = lovr::gemm_tcgen05_kernel<BN, EPI, ACT>;
+  static bool attr_set = false;
+  const int smem = lovr::GemmSmem<BN>::kTotal;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  const int m_tiles = (args.M + lovr::kBM - 1) / lovr::kBM;
+  const int n_tiles = (args.N + BN - 1) / BN;
+  const int units = args.batch * m_tiles * (n_tiles / args.n_inner);
+  const int grid = units < device_info().sms ? units : device_info().sms;
+  if (grid <= 0) return 0;
+  kern<<<grid, lovr::kGemmThreads, smem, s>>>(a, b, c, args);
+  LAUNCH_CHECK("gemm_tcgen05_kernel");
+  return 0;
+}
+
+int launch_gemm(int bn, int epi, int act, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c,
+                const lovr::GemmArgs& args, cudaStream_t s) {
+  using namespace lovr;
+  if (args.K % kBK) return fail(LOVR_E_ARG, "gemm: K=%d must be a multiple of 64", args.K);
+  if (epi == EPI_BF16 && bn == 256) {
+    switch (act) {
+      case ACT_NONE: return launch_gemm_inst<256, EPI_BF16, ACT_NONE>(a, b, c, args, s);
+      case ACT_QUICK_GELU: return launch_gemm_inst<256, EPI_BF16, ACT_QUICK_GELU>(a, b, c, args, s);
+      case ACT_GELU_ERF: return launch_gemm_inst<256, EPI_BF16, ACT_GELU_ERF>(a, b, c, args, s);
+      case ACT_GELU_TANH: return launch_gemm_inst<256, EPI_BF16, ACT_GELU_TANH>(a, b, c, args, s);
+    }
+  }
+  if (epi == EPI_RESID_F32 && bn == 256) return launch_gemm_inst<256, EPI_RESID_F32, ACT_NONE>(a, b, c, args, s);
+  if (epi == EPI_F32 && bn == 256) return launch_gemm_inst<256, EPI_F32, ACT_NONE>(a, b, c, args, s);
+  if (epi == EPI_ROWMAX && bn == 128) return launch_gemm_inst<128, EPI_ROWMAX, ACT_NONE>(a, b, c, args, s);
+  if (epi == EPI_ROWMAX && bn == 192) return launch_gemm_inst<192, EPI_ROWMAX, ACT_NONE>(a, b, c, args, s);
+  if (epi == EPI_ROWMAX && bn == 256) return launch_gemm_inst<256, EPI_ROWMAX, ACT_NONE>(a, b, c, args, s);
+  return fail(LOVR_E_UNSUPPORTED, "gemm: no instance for BN=%d epi=%d act=%d", bn, epi, act);
+}
+
+constexpr int kDenseBN = 256;
+
+// Dense layer: A [M,K] bf16 (lda), W [N,K] bf16 (ldw), C [M,N] (ldc; bf16 or fp32 by epilogue).
+int dense_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int M, int N, int K,
+               int epi, int act, const float* bias, const float* colscale, cudaStream_t s) {
+  if (N % kDenseBN) return fail(LOVR_E_ARG, "gemm: N=%d must be a multiple of %d", N, kDenseBN);
+  if (M <= 0) return 0;
+  CUtensorMap ta, tb, tc;
+  int rc;
+  if ((rc = make_tmap(&ta, A, 2, K, M, 1, lda, static_cast<uint64_t>(lda) * M, 64, lovr::kBM))) return rc;
+  if ((rc = make_tmap(&tb, W, 2, K, N, 1, ldw, static_cast<uint64_t>(ldw) * N, 64, kDenseBN))) return rc;
+  if (epi == lovr::EPI_BF16) {
+    if ((rc = make_tmap(&tc, C, 2, N, M, 1, ldc, static_cast<uint64_t>(ldc) * M, 64, 32))) return rc;
+  } else {
+    if ((rc = make_tmap(&tc, C, 4, N, M, 1, ldc, static_cast<uint64_t>(ldc) * M, 32, 32))) return rc;
+  }
+  lovr::GemmArgs g{};
+  g.M = M; g.N = N; g.K = K; g.batch = 1; g.n_inner = 1;
+  g.bias = bias; g.colscale = colscale; g.rowscale = nullptr; g.rowmax = nullptr; g.n_valid = N;
+  return launch_gemm(kDenseBN, epi, act, ta, tb, tc, g, s);
+}
+
+// ------------------------------------------------------------------------------------ row-wise launches
+template <typename F4, typename F3>
+int dispatch_width(int D, F4 f1024, F3 f768) {
+  if (D == 1024) return f1024();
+  if (D == 768) return f768();
+  return fail(LOVR_E_UNSUPPORTED, "hidden size %d not instantiated (1024, 768)", D);
+}
+
+int launch_layernorm(const float* x, const float* g, const float* b, float eps, void* y, int64_t rows, int D,
+                     cudaStream_t s) {
+  if (rows <= 0) return 0;
+  const int wpb = 8;
+  const unsigned grid = static_cast<unsigned>((rows + wpb - 1) / wpb);
+  auto y16 = static_cast<__nv_bfloat16*>(y);
+  int rc = dispatch_width(
+      D,
+      [&] { lovr::layernorm_bf16_kernel<8><<<grid, wpb * 32, 0, s>>>(x, g, b, eps, y16, rows); return 0; },
+      [&] { lovr::layernorm_bf16_kernel<6><<<grid, wpb * 32, 0, s>>>(x, g, b, eps, y16, rows); return 0; });
+  if (rc) return rc;
+  LAUNCH_CHECK("layernorm_bf16_kernel");
+  return 0;
+}
+
+int launch_attention(const void* qkv, void* out, int n_img, int T, int H, int impl, cudaStream_t s) {
+  if (n_img <= 0) return 0;
+  const int D = H * 64;
+  if (impl == LOVR_ATTN_SIMT_CHECK) {
+    const size_t smem = lovr::attn_simt_smem_bytes(T);
+    static size_t set_for = 0;
+    if (smem > set_for) {
+      CUDA_TRY(cudaFuncSetAttribute(lovr::attention_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(smem)));
+      set_for = smem;
+    }
+    lovr::attention_simt_kernel<<<n_img * H, lovr::kSimtAttnWarps * 32, smem, s>>>(
+        static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), T, H, 0.125f);
+    LAUNCH_CHECK("attention_simt_kernel");
+    return 0;
+  }
+  const int nb = (T + 127) / 128;
+  if (nb > lovr::kAttnMaxBlocks) return fail(LOVR_E_UNSUPPORTED, "attention: T=%d > 640 tokens", T);
+  const int rem = T - 128 * (nb - 1);
+  lovr::AttnArgs a{};
+  a.T = T; a.H = H; a.nb = nb; a.last_w = (rem + 15) / 16 * 16; a.scale = 0.125f;
+  a.out = static_cast<__nv_bfloat16*>(out);
+  CUtensorMap tq;
+  int rc;
+  if ((rc = make_tmap(&tq, qkv, 2, 3 * D, T, n_img, 3 * D, static_cast<uint64_t>(3) * D * T, 64, 128))) return rc;
+  const size_t smem = lovr::attn_smem_bytes(nb);
+  static size_t set_for = 0;
+  if (smem > set_for) {
+    CUDA_TRY(cudaFuncSetAttribute(lovr::attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem)));
+    set_for = smem;
+  }
+  lovr::attention_tcgen05_kernel<<<n_img * H, lovr::kAttnThreads, smem, s>>>(tq, a);
+  LAUNCH_CHECK("attention_tcgen05_kernel");
+  return 0;
+}
+
+int launch_im2col(const void* pixels, int dt, void* cols, int n_img, int R, int P, int Kpad, cudaStream_t s) {
+  if (n_img <= 0) return 0;
+  const int G = R / P;
+  const size_t total = static_cast<size_t>(n_img) * G * G * Kpad;
+  const unsigned grid = static_cast<unsigned>(std::min<size_t>((total + 255) / 256, 148 * 32));
+  lovr::im2col_kernel<<<grid, 256, 0, s>>>(pixels, dt, static_cast<__nv_bfloat16*>(cols), n_img, R, P, G, Kpad);
+  LAUNCH_CHECK("im2col_kernel");
+  return 0;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+// ====================================================================================== tower
+struct lovr_tower {
+  lovr_tower_config cfg;
+  lovr_tower_weights w;
+  std::vector<lovr_layer_weights> layers;
+  int max_batch;
+  int T, G;
+  // workspace carve-up
+  float* x;      // [B*T, D] fp32 residual stream
+  void* ln;      // [B*T, D] bf16: LayerNorm output / attention output
+  void* big;     // [B*T, I] bf16: qkv (first 3D columns' worth) or MLP hidden; patch-embed scratch
+};
+
+namespace {
+struct WsLayout {
+  size_t x, ln, big, total;
+};
+WsLayout ws_layout(const lovr_tower_config& c, int B) {
+  const int G = c.image_size / c.patch_size;
+  const size_t T = static_cast<size_t>(G) * G + (c.has_cls ? 1 : 0);
+  const size_t M = T * B;
+  WsLayout l;
+  l.x = 0;
+  size_t off = align_up(M * c.hidden_size * 4, 1024);
+  l.ln = off;
+  off += align_up(M * c.hidden_size * 2, 1024);
+  l.big = off;
+  size_t big = M * static_cast<size_t>(c.intermediate_size) * 2;
+  const size_t qkv = M * 3 * static_cast<size_t>(c.hidden_size) * 2;
+  const size_t pe = align_up(static_cast<size_t>(B) * G * G * c.patch_k_padded * 2, 1024) +
+                    static_cast<size_t>(B) * G * G * c.hidden_size * 4;
+  if (qkv > big) big = qkv;
+  if (pe > big) big = pe;
+  off += align_up(big, 1024);
+  l.total = off;
+  return l;
+}
+}  // namespace
+
+extern "C" {
+
+int lovr_abi_version(void) { return LOVR_ABI_VERSION; }
+const char* lovr_last_error(void) { return g_err.c_str(); }
+uint64_t lovr_launch_count(void) { return g_launches; }
+
+size_t lovr_tower_workspace_bytes(const lovr_tower_config* cfg, int32_t max_batch) {
+  if (!cfg || max_batch <= 0) return 0;
+  return ws_layout(*cfg, max_batch).total;
+}
+
+int lovr_tower_create(lovr_tower_t** out, const lovr_tower_config* cfg, const lovr_tower_weights* w, void* workspace,
+                      size_t workspace_bytes, int32_t max_batch) {
+  if (!out || !cfg || !w || !workspace) return fail(LOVR_E_ARG, "tower_create: null argument");
+  if (int rc = require_device()) return rc;
+  if (cfg->hidden_size != cfg->num_heads * 64) return fail(LOVR_E_UNSUPPORTED, "head_dim must be 64");
+  if (cfg->hidden_size != 1024 && cfg->hidden_size != 768) return fail(LOVR_E_UNSUPPORTED, "hidden size %d", cfg->hidden_size);
+  if (cfg->image_size % cfg->patch_size) return fail(LOVR_E_ARG, "image size not a multiple of the patch size");
+  if (cfg->patch_k_padded % 64 || cfg->patch_k_padded < 3 * cfg->patch_size * cfg->patch_size)
+    return fail(LOVR_E_ARG, "patch_k_padded must be a multiple of 64 covering 3*P*P");
+  if (cfg->intermediate_size % 256 || cfg->hidden_size % 256) return fail(LOVR_E_UNSUPPORTED, "widths must be multiples of 256");
+  const WsLayout l = ws_layout(*cfg, max_batch);
+  if (workspace_bytes < l.total) return fail(LOVR_E_NOMEM, "workspace %zu < required %zu", workspace_bytes, l.total);
+  if (reinterpret_cast<uintptr_t>(workspace) & 1023) return fail(LOVR_E_ARG, "workspace must be 1024-byte aligned");
+  auto* t = new lovr_tower();
+  t->cfg = *cfg;
+  t->w = *w;
+  t->layers.assign(w->layers_host, w->layers_host + cfg->num_layers);
+  t->w.layers_host = t->layers.data();
+  t->max_batch = max_batch;
+  t->G = cfg->image_size / cfg->patch_size;
+  t->T = t->G * t->G + (cfg->has_cls ? 1 : 0);
+  if (t->T > 640) {
+    delete t;
+    return fail(LOVR_E_UNSUPPORTED, "%d tokens per image > 640", t->T);
+  }
+  auto base = static_cast<uint8_t*>(workspace);
+  t->x = reinterpret_cast<float*>(base + l.x);
+  t->ln = base + l.ln;
+  t->big = base + l.big;
+  *out = t;
+  return 0;
+}
+
+void lovr_tower_destroy(lovr_tower_t* t) { delete t; }
+
+int lovr_tower_forward(lovr_tower_t* t, const void* pixels, int32_t pixel_dtype, int32_t n_img, int32_t layers_to_run,
+                       int32_t drop_first, void* out, int32_t out_dtype, int64_t out_ld, int64_t out_col_off,
+                       int32_t attn_impl, void* stream) {
+  using namespace lovr;
+  if (!t || !pixels || !out) return fail(LOVR_E_ARG, "tower_forward: null argument");
+  if (n_img <= 0 || n_img > t->max_batch) return fail(LOVR_E_ARG, "n_img=%d outside [1,%d]", n_img, t->max_batch);
+  if (layers_to_run < 0 || layers_to_run > t->cfg.num_layers) return fail(LOVR_E_ARG, "layers_to_run=%d", layers_to_run);
+  const lovr_tower_config& c = t->cfg;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int D = c.hidden_size, I = c.intermediate_size, T = t->T, G = t->G;
+  const int M = n_img * T;
+  const int Mp = n_img * G * G;
+  int rc;
+  // ---- embeddings: im2col -> GEMM (+conv bias) -> +cls, +pos, (pre-LN)
+  void* cols = t->big;
+  float* patch_out = reinterpret_cast<float*>(static_cast<uint8_t*>(t->big) +
+                                              align_up(static_cast<size_t>(Mp) * c.patch_k_padded * 2, 1024));
+  if ((rc = launch_im2col(pixels, pixel_dtype, cols, n_img, c.image_size, c.patch_size, c.patch_k_padded, s))) return rc;
+  if ((rc = dense_gemm(cols, c.patch_k_padded, t->w.patch_w, c.patch_k_padded, patch_out, D, Mp, D, c.patch_k_padded,
+                       EPI_F32, ACT_NONE, t->w.patch_b, nullptr, s)))
+    return rc;
+  {
+    const int wpb = 8;
+    const unsigned grid = static_cast<unsigned>((static_cast<size_t>(M) + wpb - 1) / wpb);
+    rc = dispatch_width(
+        D,
+        [&] {
+          embed_finalize_kernel<8><<<grid, wpb * 32, 0, s>>>(patch_out, t->w.cls, t->w.pos, t->w.pre_ln_w, t->w.pre_ln_b,
+                                                             c.ln_eps, t->x, n_img, T, c.has_cls);
+          return 0;
+        },
+        [&] {
+          embed_finalize_kernel<6><<<grid, wpb * 32, 0, s>>>(patch_out, t->w.cls, t->w.pos, t->w.pre_ln_w, t->w.pre_ln_b,
+                                                             c.ln_eps, t->x, n_img, T, c.has_cls);
+          return 0;
+        });
+    if (rc) return rc;
+    LAUNCH_CHECK("embed_finalize_kernel");
+  }
+  // ---- encoder layers
+  for (int li = 0; li < layers_to_run; ++li) {
+    const lovr_layer_weights& lw = t->layers[li];
+    if ((rc = launch_layernorm(t->x, lw.ln1_w, lw.ln1_b, c.ln_eps, t->ln, M, D, s))) return rc;
+    if ((rc = dense_gemm(t->ln, D, lw.qkv_w, D, t->big, 3 * D, M, 3 * D, D, EPI_BF16, ACT_NONE, lw.qkv_b, nullptr, s)))
+      return rc;
+    if ((rc = launch_attention(t->big, t->ln, n_img, T, c.num_heads, attn_impl, s))) return rc;
+    if ((rc = dense_gemm(t->ln, D, lw.o_w, D, t->x, D, M, D, D, EPI_RESID_F32, ACT_NONE, lw.o_b, lw.ls1, s))) return rc;
+    if ((rc = launch_layernorm(t->x, lw.ln2_w, lw.ln2_b, c.ln_eps, t->ln, M, D, s))) return rc;
+    if ((rc = dense_gemm(t->ln, D, lw.fc1_w, D, t->big, I, M, I, D, EPI_BF16, c.act, lw.fc1_b, nullptr, s))) return rc;
+    if ((rc = dense_gemm(t->big, I, lw.fc2_w, I, t->x, D, M, D, I, EPI_RESID_F32, ACT_NONE, lw.fc2_b, lw.ls2, s)))
+      return rc;
+  }
+  // ---- feature_select + cast into the caller's layout
+  {
+    const int drop = drop_first ? 1 : 0;
+    const size_t rows = static_cast<size_t>(n_img) * (T - drop);
+    const int wpb = 8;
+    const unsigned grid = static_cast<unsigned>((rows + wpb - 1) / wpb);
+    rc = dispatch_width(
+        D,
+        [&] {
+          select_cast_kernel<8><<<grid, wpb * 32, 0, s>>>(t->x, out, out_dtype, n_img, T, drop, static_cast<int>(out_ld),
+                                                          static_cast<int>(out_col_off));
+          return 0;
+        },
+        [&] {
+          select_cast_kernel<6><<<grid, wpb * 32, 0, s>>>(t->x, out, out_dtype, n_img, T, drop, static_cast<int>(out_ld),
+                                                          static_cast<int>(out_col_off));
+          return 0;
+        });
+    if (rc) return rc;
+    LAUNCH_CHECK("select_cast_kernel");
+  }
+  return 0;
+}
+
+// ====================================================================================== building blocks
+int lovr_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int32_t M, int32_t N,
+                   int32_t K, int32_t epi, int32_t act, const float* bias, const float* colscale, void* stream) {
+  if (int rc = require_device()) return rc;
+  if (!A || !W || !C) return fail(LOVR_E_ARG, "gemm: null pointer");
+  if (epi < 0 || epi > LOVR_EPI_F32) return fail(LOVR_E_ARG, "gemm: epilogue %d", epi);
+  if (epi != LOVR_EPI_BF16 && act != LOVR_ACT_NONE) return fail(LOVR_E_ARG, "gemm: activation only with the bf16 epilogue");
+  return dense_gemm(A, lda, W, ldw, C, ldc, M, N, K, epi, act, bias, colscale, static_cast<cudaStream_t>(stream));
+}
+
+int lovr_layernorm_bf16(const float* x, const float* gamma, const float* beta, float eps, void* y, int64_t rows,
+                        int32_t D, void* stream) {
+  if (int rc = require_device()) return rc;
+  return launch_layernorm(x, gamma, beta, eps, y, rows, D, static_cast<cudaStream_t>(stream));
+}
+
+int lovr_attention(const void* qkv, void* out, int32_t n_img, int32_t T, int32_t H, int32_t impl, void* stream) {
+  if (int rc = require_device()) return rc;
+  return launch_attention(qkv, out, n_img, T, H, impl, static_cast<cudaStream_t>(stream));
+}
+
+int lovr_im2col(const void* pixels, int32_t pixel_dtype, void* cols, int32_t n_img, int32_t image_size, int32_t patch,
+                int32_t k_padded, void* stream) {
+  if (int rc = require_device()) return rc;
+  return launch_im2col(pixels, pixel_dtype, cols, n_img, image_size, patch, k_padded, static_cast<cudaStream_t>(stream));
+}
+
+// ====================================================================================== A score
+namespace {
+struct AScoreLayout {
+  size_t inv_o, inv_r, rowmax, split_o, split_r, total;
+};
+AScoreLayout a_layout(int dtype, int64_t n, int x, int y, int D) {
+  AScoreLayout l{};
+  size_t off = 0;
+  l.inv_o = off; off += align_up(static_cast<size_t>(n) * x * 4, 1024);
+  l.inv_r = off; off += align_up(static_cast<size_t>(n) * y * 4, 1024);
+  l.rowmax = off; off += align_up(static_cast<size_t>(n) * x * 4, 1024);
+  if (dtype == LOVR_DT_F32) {
+    l.split_o = off; off += align_up(static_cast<size_t>(n) * x * 3 * D * 2, 1024);
+    l.split_r = off; off += align_up(static_cast<size_t>(n) * y * 3 * D * 2, 1024);
+  }
+  l.total = off;
+  return l;
+}
+int pick_bn(int y) {
+  int best = 128;
+  long best_waste = -1;
+  for (int bn : {128, 192, 256}) {
+    const long waste = static_cast<long>((y + bn - 1) / bn) * bn - y;
+    if (best_waste < 0 || waste < best_waste || (waste == best_waste && bn > best)) {
+      best = bn;
+      best_waste = waste;
+    }
+  }
+  return best;
+}
+}  // namespace
+
+size_t lovr_a_score_workspace_bytes(int32_t dtype, int64_t n_pairs, int32_t x, int32_t y, int32_t D) {
+  return a_layout(dtype, n_pairs, x, y, D).total;
+}
+
+int lovr_a_score_maxcos(const void* other, const void* ref, int32_t dtype, int64_t n_pairs, int32_t x, int32_t y,
+                        int32_t D, float* pair_score, void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace lovr;
+  if (int rc = require_device()) return rc;
+  if (!other || !ref || !pair_score || !workspace) return fail(LOVR_E_ARG, "a_score: null pointer");
+  if (dtype != LOVR_DT_BF16 && dtype != LOVR_DT_F32) return fail(LOVR_E_UNSUPPORTED, "a_score: dtype %d (bf16 or fp32)", dtype);
+  if (D % 64 || x <= 0 || y <= 0 || n_pairs <= 0) return fail(LOVR_E_ARG, "a_score: need D %% 64 == 0 and positive sizes");
+  if (n_pairs > 0x7fffffff / ((x + 127) / 128)) return fail(LOVR_E_ARG, "a_score: too many pairs for one call");
+  const AScoreLayout l = a_layout(dtype, n_pairs, x, y, D);
+  if (workspace_bytes < l.total) return fail(LOVR_E_NOMEM, "a_score workspace %zu < %zu", workspace_bytes, l.total);
+  if (reinterpret_cast<uintptr_t>(workspace) & 1023) return fail(LOVR_E_ARG, "workspace must be 1024-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  auto base = static_cast<uint8_t*>(workspace);
+  float* inv_o = reinterpret_cast<float*>(base + l.inv_o);
+  float* inv_r = reinterpret_cast<float*>(base + l.inv_r);
+  float* rowmax = reinterpret_cast<float*>(base + l.rowmax);
+  const size_t rows_o = static_cast<size_t>(n_pairs) * x, rows_r = static_cast<size_t>(n_pairs) * y;
+  const int wpb = 8;
+  const void* a_ptr = other;
+  const void* b_ptr = ref;
+  int K = D;
+  if (dtype == LOVR_DT_BF16) {
+    rownorm_inv_bf16_kernel<<<static_cast<unsigned>((rows_o + wpb - 1) / wpb), wpb * 32, 0, s>>>(
+        static_cast<const __nv_bfloat16*>(other), inv_o, rows_o, D);
+    LAUNCH_CHECK("rownorm_inv_bf16_kernel");
+    rownorm_inv_bf16_kernel<<<static_cast<unsigned>((rows_r + wpb - 1) / wpb), wpb * 32, 0, s>>>(
+        static_cast<const __nv_bfloat16*>(ref), inv_r, rows_r, D);
+    LAUNCH_CHECK("rownorm_inv_bf16_kernel");
+  } else {
+    auto so = reinterpret_cast<__nv_bfloat16*>(base + l.split_o);
+    auto sr = reinterpret_cast<__nv_bfloat16*>(base + l.split_r);
+    split3_kernel<<<static_cast<unsigned>((rows_o + wpb - 1) / wpb), wpb * 32, 0, s>>>(
+        static_cast<const float*>(other), so, inv_o, rows_o, D, 0);
+    LAUNCH_CHECK("split3_kernel");
+    split3_kernel<<<static_cast<unsigned>((rows_r + wpb - 1) / wpb), wpb * 32, 0, s>>>(
+        static_cast<const float*>(ref), sr, inv_r, rows_r, D, 1);
+    LAUNCH_CHECK("split3_kernel");
+    a_ptr = so;
+    b_ptr = sr;
+    K = 3 * D;
+  }
+  const int bn = pick_bn(y);
+  CUtensorMap ta, tb;
+  int rc;
+  if ((rc = make_tmap(&ta, a_ptr, 2, K, x, n_pairs, K, static_cast<uint64_t>(K) * x, 64, kBM))) return rc;
+  if ((rc = make_tmap(&tb, b_ptr, 2, K, y, n_pairs, K, static_cast<uint64_t>(K) * y, 64, bn))) return rc;
+  GemmArgs g{};
+  g.M = x; g.N = y; g.K = K; g.batch = static_cast<int>(n_pairs);
+  g.n_inner = (y + bn - 1) / bn;
+  g.bias = nullptr; g.colscale = inv_r; g.rowscale = inv_o; g.rowmax = rowmax; g.n_valid = y;
+  if ((rc = launch_gemm(bn, EPI_ROWMAX, ACT_NONE, ta, tb, ta /*unused*/, g, s))) return rc;
+  pair_mean_kernel<<<static_cast<unsigned>(n_pairs), 256, 0, s>>>(rowmax, pair_score, x);
+  LAUNCH_CHECK("pair_mean_kernel");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,115 @@
+"""Parity of each CUDA building block, called through the C ABI, against plain fp32 PyTorch on the same
+bf16-representable inputs.  Runs on the B200 box only."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from law_of_vision_representation_in_mllms_b200 import _lib
+import gpu_util as G
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _fp32_reference_math():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+    torch.cuda.synchronize()
+
+
+def _rand(shape, seed, scale=1.0, dtype=torch.bfloat16):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(*shape, generator=g, device="cuda") * scale).to(dtype)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 256, 1024), (200, 1024, 640), (577 * 3, 3072, 1024),
+                                   (1154, 768, 3072), (65, 256, 128), (4096 + 37, 4096, 1024)])
+def test_gemm_f32_epilogue(M, N, K):
+    A, W = _rand((M, K), 1), _rand((N, K), 2, 0.05)
+    bias = _rand((N,), 3, 1.0, torch.float32)
+    got = G.gemm(A, W, _lib.EPI_F32, bias=bias)
+    want = A.float() @ W.float().T + bias
+    assert G.rel_err(got, want) < 2e-6
+    assert (got - want).abs().max() < 1e-3 * want.abs().max()
+
+
+@pytest.mark.parametrize("act", [0, 1, 2, 3])
+def test_gemm_bf16_epilogue_activations(act):
+    M, N, K = 577 * 2 + 5, 1024, 1024
+    A, W = _rand((M, K), 4), _rand((N, K), 5, 0.05)
+    bias = _rand((N,), 6, 0.5, torch.float32)
+    got = G.gemm(A, W, _lib.EPI_BF16, act=act, bias=bias)
+    z = A.float() @ W.float().T + bias
+    want = [z, z * torch.sigmoid(1.702 * z), F.gelu(z), F.gelu(z, approximate="tanh")][act]
+    assert got.dtype == torch.bfloat16
+    # bf16 output rounding: 2^-9 relative per element
+    assert G.rel_err(got, want) < 3e-3
+    assert G.rel_err(got, want.to(torch.bfloat16)) < 1.5e-3
+
+
+@pytest.mark.parametrize("use_ls", [False, True])
+def test_gemm_residual_epilogue(use_ls):
+    M, N, K = 1300, 1024, 4096
+    A, W = _rand((M, K), 7), _rand((N, K), 8, 0.02)
+    bias = _rand((N,), 9, 0.5, torch.float32)
+    ls = _rand((N,), 10, 1.0, torch.float32) if use_ls else None
+    x0 = _rand((M, N), 11, 3.0, torch.float32)
+    x = x0.clone()
+    G.gemm(A, W, _lib.EPI_RESID_F32, bias=bias, colscale=ls, C_inout=x)
+    delta = A.float() @ W.float().T + bias
+    want = x0 + (delta * ls if use_ls else delta)
+    assert G.rel_err(x, want) < 2e-6
+
+
+def test_gemm_rejects_bad_shapes():
+    A, W = _rand((128, 100), 1), _rand((256, 100), 2)
+    with pytest.raises(_lib.LovrError):
+        G.gemm(A, W, _lib.EPI_F32)
+
+
+@pytest.mark.parametrize("D,eps", [(1024, 1e-5), (768, 1e-6)])
+def test_layernorm(D, eps):
+    x = _rand((1000, D), 12, 2.0, torch.float32) + 0.7
+    g, b = _rand((D,), 13, 0.2, torch.float32) + 1, _rand((D,), 14, 0.2, torch.float32)
+    got = G.layernorm(x, g, b, eps)
+    want = F.layer_norm(x, (D,), g, b, eps)
+    assert G.rel_err(got, want.to(torch.bfloat16)) < 1e-3
+    assert G.rel_err(got, want) < 3e-3
+
+
+@pytest.mark.parametrize("R,P,kpad,dtype", [(224, 14, 640, torch.float32), (336, 14, 640, torch.bfloat16),
+                                             (224, 16, 768, torch.float16)])
+def test_im2col_matches_unfold(R, P, kpad, dtype):
+    px = _rand((3, 3, R, R), 15, 1.0, dtype)
+    cols = G.im2col(px, P, kpad)
+    want = F.unfold(px.float(), kernel_size=P, stride=P).transpose(1, 2).reshape(-1, 3 * P * P)
+    assert torch.equal(cols[:, : 3 * P * P].float(), want.to(torch.bfloat16).float())
+    assert cols[:, 3 * P * P:].abs().max().item() == 0 if kpad > 3 * P * P else True
+
+
+def _torch_attention(qkv, n, T, H):
+    D = H * 64
+    q, k, v = qkv.float().view(n, T, 3, H, 64).permute(2, 0, 3, 1, 4)
+    p = torch.softmax(q @ k.transpose(-1, -2) * 0.125, dim=-1)
+    return (p @ v).transpose(1, 2).reshape(n * T, D)
+
+
+@pytest.mark.parametrize("impl", [_lib.ATTN_SIMT_CHECK, _lib.ATTN_TCGEN05])
+@pytest.mark.parametrize("n,T,H,scale", [(2, 577, 16, 1.0), (3, 257, 16, 2.0), (2, 196, 12, 1.0), (1, 50, 16, 1.0),
+                                          (1, 128, 16, 3.0), (1, 640, 16, 1.0)])
+def test_attention(impl, n, T, H, scale):
+    qkv = _rand((n * T, 3 * H * 64), 16 + T, scale)
+    got = G.attention(qkv, n, T, H, impl)
+    want = _torch_attention(qkv, n, T, H)
+    assert torch.isfinite(got.float()).all()
+    # P is rounded to bf16 before P·V on the tensor-core path; output is bf16
+    assert G.rel_err(got, want) < (4e-3 if impl == _lib.ATTN_TCGEN05 else 3e-3)
+
+
+def test_attention_tcgen05_matches_simt_check():
+    n, T, H = 4, 577, 16
+    qkv = _rand((n * T, 3 * H * 64), 99, 1.5)
+    a = G.attention(qkv, n, T, H, _lib.ATTN_TCGEN05)
+    b = G.attention(qkv, n, T, H, _lib.ATTN_SIMT_CHECK)
+    assert G.rel_err(a, b.float()) < 4e-3

@@ -1,0 +1,95 @@
+"""Vision towers on the device, through the reference-shaped Python interface (towers.py -> C ABI), against
+(a) fixtures produced by the reference wrappers themselves (tests/golden/vit_*.pt) and (b) the CPU oracle.
+Tolerance: north_star asks 1e-3 relative for the bf16 path; measured as ||got-want||_F / ||want||_F."""
+import os
+import types
+
+import pytest
+import torch
+
+from law_of_vision_representation_in_mllms_b200 import _lib, specs as S, towers
+from law_of_vision_representation_in_mllms_b200.weights import canonical_weights, synthetic_images
+from oracle import vit_oracle
+from oracle.make_golden import VIT_CASES, vit_case_inputs
+import gpu_util as G
+
+pytestmark = pytest.mark.gpu
+REL_TOL = 1e-3
+
+_CLS = {S.FAMILY_CLIP: towers.CLIPVisionTower, S.FAMILY_DINOV2: towers.DinoV2VisionTower,
+        S.FAMILY_SIGLIP: towers.SigLipVisionTower}
+
+
+def _build(case, attn_impl=_lib.ATTN_TCGEN05):
+    name, key, nl, size, n, sl, sf = case
+    spec, sd, imgs = vit_case_inputs(case)
+    args = types.SimpleNamespace(mm_vision_select_layer=sl, mm_vision_select_feature=sf, lovr_spec=spec,
+                                 lovr_state_dict=sd, lovr_image_size=size, lovr_max_batch=4)
+    tower = _CLS[spec.family](key, args)
+    tower._attn_impl = attn_impl
+    return tower, spec, sd, imgs
+
+
+@pytest.mark.parametrize("case", VIT_CASES, ids=[c[0] for c in VIT_CASES])
+def test_tower_matches_reference_fixture(case, golden_dir):
+    name = case[0]
+    rec = torch.load(os.path.join(golden_dir, f"vit_{name}.pt"))
+    tower, spec, sd, imgs = _build(case)
+    out = tower(imgs.cuda())
+    assert out.dtype == imgs.dtype and tuple(out.shape) == tuple(rec["shape"])
+    got = out[:, rec["rows"]].cpu()
+    rel = G.rel_err(got, rec["values"])
+    print(f"{name}: rel {rel:.3e}")
+    assert rel < REL_TOL, rel
+    assert torch.allclose(out.float().flatten(1).norm(dim=1).cpu(), rec["fro"], rtol=2e-3)
+
+
+@pytest.mark.parametrize("cname", ["clip336_l3", "dinov2_336_l3", "siglip224_l3"])
+def test_tower_matches_oracle_full_tensor_and_simt_attention(cname):
+    case = next(c for c in VIT_CASES if c[0] == cname)
+    name, key, nl, size, n, sl, sf = case
+    tower, spec, sd, imgs = _build(case)
+    cw = canonical_weights(spec, sd, image_size=size)
+    want = vit_oracle.tower_forward(cw, spec.at_resolution(size), imgs, sl, tower.select_feature)
+    out = tower(imgs.cuda()).cpu()
+    assert G.rel_err(out, want) < REL_TOL
+    tower._attn_impl = _lib.ATTN_SIMT_CHECK
+    out2 = tower(imgs.cuda()).cpu()
+    assert G.rel_err(out2, want) < REL_TOL
+
+
+def test_caller_dtype_list_input_and_batch_chunking():
+    case = next(c for c in VIT_CASES if c[0] == "clip336_l3")
+    tower, spec, sd, _ = _build(case)
+    imgs = synthetic_images(6, 336, seed=5)           # > lovr_max_batch=4 -> two native calls
+    ref = tower(imgs.cuda())
+    for dt in (torch.bfloat16, torch.float16):
+        o = tower(imgs.cuda().to(dt))
+        assert o.dtype == dt
+        assert G.rel_err(o, ref) < 6e-3
+    lst = tower([im for im in imgs.cuda()])
+    assert isinstance(lst, list) and tuple(lst[0].shape) == (1, 576, 1024)
+    assert torch.equal(torch.cat(lst), ref)          # batch-size independent results
+
+
+def test_select_feature_and_errors():
+    case = next(c for c in VIT_CASES if c[0] == "clip224_l3_clspatch")
+    tower, spec, sd, imgs = _build(case)
+    tower.select_feature = "bogus"
+    with pytest.raises(ValueError, match="Unexpected select feature"):
+        tower(imgs.cuda())
+    tower.select_feature = "patch"
+    with pytest.raises(ValueError):                    # CLIP is fixed-resolution (HF raises on mismatch)
+        tower(synthetic_images(1, 336).cuda())
+
+
+def test_dual_tower_concat_matches_separate_towers():
+    c1 = next(c for c in VIT_CASES if c[0] == "clip336_l3")
+    c2 = next(c for c in VIT_CASES if c[0] == "dinov2_336_l3")
+    t1, _, _, im1 = _build(c1)
+    t2, _, _, im2 = _build(c2)
+    both = torch.nn.ModuleList([t1, t2])
+    fused = towers.encode_images(both, [im1.cuda(), im2.cuda()])
+    assert tuple(fused.shape) == (2, 576, 2048)
+    assert torch.equal(fused[..., :1024], t1(im1.cuda()))
+    assert torch.equal(fused[..., 1024:], t2(im2.cuda()))
