@@ -1,0 +1,274 @@
+#!/usr/bin/env python
+"""Headline benchmark (BASELINE.json): images/sec of CLIP ViT-L/14-336 patch-feature extraction on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's algorithm on the host CPU cores
+
+A step = one tower forward over one batch of `--batch` synthetic 336px images (config[1]: "CLIP ViT-L/14-336,
+10k synthetic 336px images, 1xB200 feature extract"; 10k images = 10000/batch steps).  Weights: seeded HF-init-style
+random weights of the real architecture (no checkpoints offline).  `value` = whole-job images/s with inputs already
+resident in HBM; `e2e` = the same through the public extractor (pinned host pixels -> H2D -> towers -> D2H features).
+Under torchrun every rank runs its own shard of images (weak scaling, no data-path collective); timing is
+CUDA events between barriers, max over ranks.  One JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TOWER = "openai/clip-vit-large-patch14-336"
+R, T_PATCH, D = 336, 576, 1024
+# SURVEY.md §8d / BASELINE.md §4: algorithmic work per image, layers 1-23 + patch embed, T=577
+FLOPS_PER_IMAGE = 366.03e9
+METRIC = "images/sec ViT-L/14-336 extract"
+WORKLOAD = "CLIP ViT-L/14-336, 10k synthetic 336px images, 1xB200 feature extract (configs[1])"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(tflops=float(d.get("bf16_tflops_sustained", d.get("bf16_tflops"))), source="measured (MEASURED_PEAKS.json, sustained)")
+    return dict(tflops=1400.0, source="fallback (B200_PROFILING.md sustained)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        sm = sorted(int(r[1]) for r in self.rows if len(r) >= 8 and r[1].isdigit())
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        mx = [int(r[2]) for r in self.rows if len(r) >= 8 and r[2].isdigit()]
+        pw = [float(r[3]) for r in self.rows if len(r) >= 8 and r[3].replace(".", "").isdigit()]
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    power_w_max=max(pw) if pw else None, samples=len(sm), reasons=sorted(reasons))
+
+
+def cpu_reference_leg(n_images, threads):
+    """The reference's algorithm for this path on the host: the fp32 CPU restatement (oracle/vit_oracle.py) of the HF
+    CLIPVisionModel forward the reference wrappers drive (clip_encoder.py:39-51).  `kind` = "port": the reference's own
+    Python files are not present on the GPU box.  Returns images/s over a bounded sample."""
+    import torch
+    from law_of_vision_representation_in_mllms_b200.specs import TOWER_SPECS
+    from law_of_vision_representation_in_mllms_b200.weights import canonical_weights, synthetic_images, synthetic_state_dict
+    from oracle import vit_oracle
+    torch.set_num_threads(threads)
+    spec = TOWER_SPECS[TOWER]
+    cw = canonical_weights(spec, synthetic_state_dict(spec, seed=0, style="hf_init"))
+    imgs = synthetic_images(n_images, R, seed=1234)
+    vit_oracle.tower_forward(cw, spec, imgs[:1])            # warm-up (allocator, thread pool)
+    t0 = time.perf_counter()
+    out = vit_oracle.tower_forward(cw, spec, imgs)
+    dt = time.perf_counter() - t0
+    assert tuple(out.shape) == (n_images, T_PATCH, D)
+    return n_images / dt, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_step = args.cpu_images
+    rates = []
+    for _ in range(args.warmup and 1):
+        cpu_reference_leg(1, cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r, _ = cpu_reference_leg(per_step, cores)
+        rates.append(r)
+    wall = time.perf_counter() - t0
+    v = sum(rates) / len(rates)
+    line = dict(impl="reference", metric=METRIC, value=v, unit="images/s", n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=1e3 * wall / args.steps, higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload=WORKLOAD, tower=TOWER, sample=f"{per_step} images per step on the host CPU"),
+                cpu_baseline=dict(value=v, unit="images/s", cores=cores, kind="port",
+                                  sample=f"{per_step} synthetic 336px images per step, fp32, torch CPU, {cores} threads"),
+                e2e=dict(value=v, unit="images/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="images per step per GPU")
+    ap.add_argument("--chunk", type=int, default=64, help="images per native tower call")
+    ap.add_argument("--cpu-images", type=int, default=2, help="images per CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-a-score", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    from law_of_vision_representation_in_mllms_b200 import _lib, a_score as A, extract as X
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback); use --impl reference for the CPU leg")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ex = X.build_extractor(TOWER, chunk=args.chunk, lovr_max_batch=args.chunk, lovr_device=dev,
+                           lovr_state_dict=None, lovr_seed=0)
+    tower = ex.towers[0]
+    B = args.batch
+    # ---- inputs: several distinct batches so every step reads pixels that are not L2-resident (B*677 KB >> L2 anyway)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    n_in = 3
+    dev_px = [torch.randn(B, 3, R, R, generator=g, device=dev).to(torch.bfloat16) for _ in range(n_in)]
+    dev_out = torch.empty(B, T_PATCH, D, dtype=torch.bfloat16, device=dev)
+    host_px = [p.cpu().pin_memory() for p in dev_px[:2]]
+    host_out = torch.empty(B, T_PATCH, D, dtype=torch.bfloat16).pin_memory()
+
+    def step_resident(i):
+        tower.forward_into(dev_px[i % n_in], dev_out, 0)
+
+    def step_e2e(i):
+        ex.run(host_px[i % 2], host_out)
+
+    def timed(step_fn, steps, warmup, profile=False):
+        for i in range(warmup):
+            step_fn(i)
+        barrier()
+        sampler = ClockSampler(local_rank) if (rank == 0 and profile) else None
+        if sampler:
+            sampler.start()
+        launches0 = _lib.launch_count()
+        if profile:
+            _lib.prof_read()
+            _lib.prof_enable(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            step_fn(warmup + i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        prof = None
+        if profile:
+            _lib.prof_enable(False)
+            prof = _lib.prof_read()
+        clocks = sampler.stop() if sampler else None
+        launches = _lib.launch_count() - launches0
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms, launches, prof, clocks
+
+    ms, launches, prof, clocks = timed(step_resident, args.steps, max(args.warmup, 3), profile=True)
+    value = world * B * args.steps / (ms / 1e3)
+    ms_e2e, _, _, _ = timed(step_e2e, args.steps, max(args.warmup, 3))
+    e2e_value = world * B * args.steps / (ms_e2e / 1e3)
+
+    # ---- A score at the C3 shape (10k x 576 x 1024 pairs, bf16), seconds; sharded over ranks with one all-reduce
+    a_info = None
+    if not args.no_a_score:
+        n_pairs = 10000
+        lo, hi = X.shard_range(n_pairs, rank, world)
+        ga = torch.Generator(device=dev).manual_seed(11 + rank)
+        o = torch.randn(hi - lo, T_PATCH, D, generator=ga, device=dev).to(torch.bfloat16)
+        r_ = (0.5 * o.float() + torch.randn(hi - lo, T_PATCH, D, generator=ga, device=dev)).to(torch.bfloat16)
+        A.a_score_pairs(o[:64], r_[:64])
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        s = A.a_score_pairs(o, r_).double().sum().reshape(1)
+        if world > 1:
+            dist.all_reduce(s)                       # the single collective of the score path
+        e1.record()
+        barrier()
+        a_ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(a_ms, op=dist.ReduceOp.MAX)
+        a_info = dict(config="A-score max-cos over 10k x 576 x 1024 bf16 pairs (configs[2])", seconds=a_ms.item() / 1e3,
+                      mean_a=s.item() / n_pairs, hbm_gbs=2 * n_pairs * T_PATCH * D * 2 / (a_ms.item() / 1e3) / 1e9 / world)
+        del o, r_
+
+    if rank == 0:
+        peaks = measured_peaks()
+        gemm_ms, gemm_flops, gemm_launches = prof
+        achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+        line = dict(
+            metric=METRIC, value=value, unit="images/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+            ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
+            data="synthetic",
+            config=dict(workload=WORKLOAD, tower=TOWER, images_per_step_per_gpu=B, native_chunk=args.chunk,
+                        weights="seeded HF-init-style random weights (weights.synthetic_state_dict style=hf_init)",
+                        l2="inputs larger than L2: each step reads a different %d MB pixel batch" % (B * 3 * R * R * 2 // 2**20),
+                        parallelism=f"dp{world} (images sharded, no data-path collective)"),
+            gpu_launches=launches,
+            clocks=clocks,
+            e2e=dict(value=e2e_value, unit="images/s", ms_per_step=ms_e2e / args.steps,
+                     h2d_bytes_per_step=B * 3 * R * R * 2, d2h_bytes_per_step=B * T_PATCH * D * 2,
+                     api="extract.FeatureExtractor.run (pinned host pixels -> device -> pinned host features)"),
+            roofline=dict(bound="tensor", kernel="gemm_tcgen05_kernel (all dense layers)", achieved=achieved,
+                          peak=peaks["tflops"], unit="TFLOP/s", frac=achieved / peaks["tflops"], peak_source=peaks["source"],
+                          launches=gemm_launches, gemm_share_of_step=gemm_ms / ms, traffic=None,
+                          whole_step_tflops=value / world * FLOPS_PER_IMAGE / 1e12),
+        )
+        if a_info:
+            line["a_score"] = a_info
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            v, dt = cpu_reference_leg(args.cpu_images, cores)
+            line["cpu_baseline"] = dict(value=v, unit="images/s", cores=cores, kind="port",
+                                        sample=f"{args.cpu_images} synthetic 336px images, fp32 oracle restatement of the "
+                                               f"HF CLIP forward, {dt:.1f} s")
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

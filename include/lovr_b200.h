@@ -36,6 +36,11 @@ int lovr_abi_version(void);
 const char* lovr_last_error(void);
 /* number of kernels this library has launched on the calling thread since load (bench.py's gpu_launches) */
 uint64_t lovr_launch_count(void);
+/* Live roofline measurement: while enabled, every tcgen05 GEMM launch is bracketed by CUDA events on its launch
+ * stream; lovr_prof_read() synchronises on them, returns the summed duration (ms), the summed algorithmic FLOPs
+ * (2*M*N*K per launch) and the launch count since the last read, and resets the accumulator. */
+void lovr_prof_enable(int32_t on);
+int lovr_prof_read(double* gemm_ms, double* gemm_flops, uint64_t* gemm_launches);
 
 /* ---------------------------------------------------------------------------------------------------
  * Vision tower (replaces the arithmetic behind CLIPVisionTower.forward / DinoV2VisionTower.forward /

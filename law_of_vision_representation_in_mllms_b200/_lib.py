@@ -16,7 +16,7 @@ ATTN_TCGEN05, ATTN_SIMT_CHECK = 0, 1
 
 # every symbol include/lovr_b200.h declares (tests/test_abi.py checks the library exports all of them)
 EXPORTS = [
-    "lovr_abi_version", "lovr_last_error", "lovr_launch_count",
+    "lovr_abi_version", "lovr_last_error", "lovr_launch_count", "lovr_prof_enable", "lovr_prof_read",
     "lovr_tower_workspace_bytes", "lovr_tower_create", "lovr_tower_destroy", "lovr_tower_forward",
     "lovr_gemm_bf16", "lovr_layernorm_bf16", "lovr_attention", "lovr_im2col",
     "lovr_a_score_workspace_bytes", "lovr_a_score_maxcos",
@@ -60,6 +60,10 @@ def lib():
     L.lovr_abi_version.restype = C.c_int
     L.lovr_last_error.restype = C.c_char_p
     L.lovr_launch_count.restype = C.c_uint64
+    L.lovr_prof_enable.restype = None
+    L.lovr_prof_enable.argtypes = [i32]
+    L.lovr_prof_read.restype = C.c_int
+    L.lovr_prof_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     L.lovr_tower_workspace_bytes.restype = sz
     L.lovr_tower_workspace_bytes.argtypes = [C.POINTER(TowerConfig), i32]
     L.lovr_tower_create.restype = C.c_int
@@ -92,6 +96,17 @@ def check(rc, what=""):
 
 def launch_count():
     return int(lib().lovr_launch_count())
+
+
+def prof_enable(on):
+    lib().lovr_prof_enable(1 if on else 0)
+
+
+def prof_read():
+    """-> (gemm_ms, gemm_flops, gemm_launches) accumulated since the last read."""
+    ms, fl, n = C.c_double(), C.c_double(), C.c_uint64()
+    check(lib().lovr_prof_read(C.byref(ms), C.byref(fl), C.byref(n)), "lovr_prof_read")
+    return ms.value, fl.value, int(n.value)
 
 
 def torch_dtype_code(dtype):

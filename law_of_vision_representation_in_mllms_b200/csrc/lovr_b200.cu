@@ -123,6 +123,47 @@ int make_tmap(CUtensorMap* m, const void* ptr, int elem_bytes, uint64_t dim0, ui
   return 0;
 }
 
+// ------------------------------------------------------------------------------------ live profiling
+// bench.py's roofline leg: CUDA events around every tcgen05 GEMM launch, on the launch stream, so the
+// per-launch duration is measured inside the timed region itself (two event records per launch).
+struct ProfRec {
+  cudaEvent_t a, b;
+  double flops;
+};
+struct Prof {
+  bool on = false;
+  std::vector<ProfRec> recs;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pool;
+  std::mutex mu;
+};
+Prof& prof() {
+  static Prof p;
+  return p;
+}
+bool prof_begin(cudaStream_t s, double flops, size_t* idx) {
+  Prof& p = prof();
+  if (!p.on) return false;
+  std::lock_guard<std::mutex> g(p.mu);
+  ProfRec r;
+  if (!p.pool.empty()) {
+    r.a = p.pool.back().first;
+    r.b = p.pool.back().second;
+    p.pool.pop_back();
+  } else {
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return false;
+  }
+  r.flops = flops;
+  cudaEventRecord(r.a, s);
+  p.recs.push_back(r);
+  *idx = p.recs.size() - 1;
+  return true;
+}
+void prof_end(cudaStream_t s, size_t idx) {
+  Prof& p = prof();
+  std::lock_guard<std::mutex> g(p.mu);
+  cudaEventRecord(p.recs[idx].b, s);
+}
+
 // ------------------------------------------------------------------------------------ GEMM launch
 template <int BN, int EPI, int ACT>
 int launch_gemm_inst(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const lovr::GemmArgs& args,
@@ -139,7 +180,10 @@ int launch_gemm_inst(const CUtensorMap& a, const CUtensorMap& b, const CUtensorM
   const int units = args.batch * m_tiles * (n_tiles / args.n_inner);
   const int grid = units < device_info().sms ? units : device_info().sms;
   if (grid <= 0) return 0;
+  size_t pidx = 0;
+  const bool profiled = prof_begin(s, 2.0 * args.M * args.N * static_cast<double>(args.K) * args.batch, &pidx);
   kern<<<grid, lovr::kGemmThreads, smem, s>>>(a, b, c, args);
+  if (profiled) prof_end(s, pidx);
   LAUNCH_CHECK("gemm_tcgen05_kernel");
   return 0;
 }
@@ -304,6 +348,33 @@ extern "C" {
 int lovr_abi_version(void) { return LOVR_ABI_VERSION; }
 const char* lovr_last_error(void) { return g_err.c_str(); }
 uint64_t lovr_launch_count(void) { return g_launches; }
+
+void lovr_prof_enable(int32_t on) {
+  Prof& p = prof();
+  std::lock_guard<std::mutex> g(p.mu);
+  p.on = on != 0;
+}
+
+int lovr_prof_read(double* gemm_ms, double* gemm_flops, uint64_t* gemm_launches) {
+  Prof& p = prof();
+  std::lock_guard<std::mutex> g(p.mu);
+  double ms = 0, fl = 0;
+  for (ProfRec& r : p.recs) {
+    cudaError_t e = cudaEventSynchronize(r.b);
+    if (e != cudaSuccess) return fail(LOVR_E_CUDA, "prof_read: %s", cudaGetErrorString(e));
+    float t = 0;
+    e = cudaEventElapsedTime(&t, r.a, r.b);
+    if (e != cudaSuccess) return fail(LOVR_E_CUDA, "prof_read: %s", cudaGetErrorString(e));
+    ms += t;
+    fl += r.flops;
+    p.pool.emplace_back(r.a, r.b);
+  }
+  if (gemm_ms) *gemm_ms = ms;
+  if (gemm_flops) *gemm_flops = fl;
+  if (gemm_launches) *gemm_launches = p.recs.size();
+  p.recs.clear();
+  return 0;
+}
 
 size_t lovr_tower_workspace_bytes(const lovr_tower_config* cfg, int32_t max_batch) {
   if (!cfg || max_batch <= 0) return 0;

@@ -147,8 +147,9 @@ class _B200VisionTower(nn.Module):
                 state_dict = torch.load(path, map_location="cpu")
                 self.weights_source = path
             else:
-                state_dict = synthetic_state_dict(self._spec, seed=getattr(self._args, "lovr_seed", 0))
-                self.weights_source = "synthetic"
+                style = getattr(self._args, "lovr_weight_style", "hf_init")
+                state_dict = synthetic_state_dict(self._spec, seed=getattr(self._args, "lovr_seed", 0), style=style)
+                self.weights_source = f"synthetic:{style}"
         self._state_dict = state_dict
         self._device = torch.device(device if device is not None else getattr(self._args, "lovr_device", "cuda"))
         self._max_batch = int(getattr(self._args, "lovr_max_batch", DEFAULT_MAX_BATCH))

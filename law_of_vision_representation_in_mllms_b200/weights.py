@@ -24,8 +24,15 @@ def _bf16_round(t):
     return t.to(torch.bfloat16).to(torch.float32)
 
 
-def synthetic_state_dict(spec: TowerSpec, seed: int = 0):
-    """Seeded random weights with HF names for `spec` (CPU fp32)."""
+def synthetic_state_dict(spec: TowerSpec, seed: int = 0, style: str = "stress"):
+    """Seeded random weights with HF names for `spec` (CPU fp32).
+
+    style="stress": wide q/k projections (sharp softmax), non-trivial LayerNorm affine, biases and
+    LayerScale everywhere — every term of the arithmetic matters and rounding errors are amplified.
+    style="hf_init": the distribution HF `_init_weights` draws (std 0.02 linears, unit LayerNorm, zero
+    biases), i.e. the "HF-initialised random weights" SURVEY.md §8d prescribes for benchmarks."""
+    if style == "hf_init":
+        return _hf_init_state_dict(spec, seed)
     g = torch.Generator(device="cpu").manual_seed(seed)
     D, I, L, P = spec.hidden_size, spec.intermediate_size, spec.num_layers, spec.patch_size
     sd = {}
@@ -93,6 +100,23 @@ def synthetic_state_dict(spec: TowerSpec, seed: int = 0):
         if spec.layerscale:
             sd[p + "layer_scale1.lambda1"] = rn(D, std=0.2, mean=1.0)
             sd[p + "layer_scale2.lambda1"] = rn(D, std=0.2, mean=1.0)
+    return sd
+
+
+def _hf_init_state_dict(spec, seed):
+    sd = synthetic_state_dict(spec, seed, style="stress")   # same keys, then overwrite the distributions
+    g = torch.Generator(device="cpu").manual_seed(seed + 7919)
+    for k, v in sd.items():
+        if k.endswith("lambda1"):
+            sd[k] = torch.ones_like(v)
+        elif "norm" in k and k.endswith(".weight") and v.dim() == 1:
+            sd[k] = torch.ones_like(v)
+        elif k.endswith(".bias"):
+            sd[k] = torch.zeros_like(v)
+        elif v.dim() >= 2 and "position" not in k and "cls_token" not in k and "mask_token" not in k:
+            sd[k] = _bf16_round(torch.randn(v.shape, generator=g) * 0.02)
+        else:                                   # class / cls / position embeddings
+            sd[k] = torch.randn(v.shape, generator=g) * 0.02
     return sd
 
 

@@ -113,6 +113,10 @@ VIT_CASES = [
     ("dinov2_336_full", "facebook/dinov2-large", None, 336, 1, -2, "patch"),
     ("siglip224_l3", "google/siglip-base-patch16-224", 3, 224, 2, -2, "cls_patch"),
     ("siglip224_full", "google/siglip-base-patch16-224", None, 224, 2, -2, "cls_patch"),
+    # "_hf" suffix: HF-init-style weights (weights.synthetic_state_dict(style="hf_init")), the benchmark weights
+    ("clip336_full_hf", "openai/clip-vit-large-patch14-336", None, 336, 1, -2, "patch"),
+    ("clip224_full_hf", "openai/clip-vit-large-patch14", None, 224, 2, -2, "patch"),
+    ("dinov2_336_full_hf", "facebook/dinov2-large", None, 336, 1, -2, "patch"),
 ]
 VIT_TOKENS = 12   # token rows kept per image
 
@@ -123,7 +127,7 @@ def vit_case_inputs(case):
     if nl is not None:
         spec = S.tiny_spec(spec, nl)
     seed = 100 + sum(map(ord, name)) % 1000
-    sd = synthetic_state_dict(spec, seed=seed)
+    sd = synthetic_state_dict(spec, seed=seed, style="hf_init" if name.endswith("_hf") else "stress")
     imgs = synthetic_images(n, size, seed=seed + 1)
     return spec, sd, imgs
 
@@ -145,14 +149,22 @@ def make_vit():
             if name == "clip336_l3":                # the list-of-3D-tensors calling convention
                 out_list = tower([im for im in imgs])
         rows = token_rows(out.shape[1])
+        ref_bf16_rel = None
+        if spec.family != S.FAMILY_SIGLIP:
+            # the reference's own reduced-precision path (tower cast to bf16: llava/feature/extract.py:228)
+            with torch.no_grad():
+                tower.vision_tower.to(torch.bfloat16)
+                o16 = tower(imgs[:1].to(torch.bfloat16)).float()
+                tower.vision_tower.to(torch.float32)
+            ref_bf16_rel = ((o16 - out[:1]).norm() / out[:1].norm()).item()
         rec = dict(case=case, shape=tuple(out.shape), rows=rows, values=out[:, rows].clone(),
                    fro=out.flatten(1).norm(dim=1), mean=out.flatten(1).mean(dim=1),
-                   abs_mean=out.abs().flatten(1).mean(dim=1))
+                   abs_mean=out.abs().flatten(1).mean(dim=1), ref_bf16_rel=ref_bf16_rel)
         if out_list is not None:
             rec["list_equal_batch"] = bool(all(torch.allclose(o[0], out[i], atol=1e-5) for i, o in enumerate(out_list)))
             rec["list_shapes"] = [tuple(o.shape) for o in out_list]
         torch.save(rec, os.path.join(GOLD, f"vit_{name}.pt"))
-        print("vit", name, tuple(out.shape), "fro", rec["fro"].tolist())
+        print("vit", name, tuple(out.shape), "fro", rec["fro"].tolist(), "ref bf16 rel", ref_bf16_rel, flush=True)
 
 
 # ----------------------------------------------------------------------------------- A score

@@ -7,7 +7,7 @@ python -c "import torch; print(torch.__version__, torch.cuda.get_device_name(0))
 for f in "$@"; do
   name=$(echo "$f" | tr '/:[]' '____')
   echo "=== $f" | tee -a gpurun_out/diag_summary.txt
-  timeout 600 python -m pytest "$f" -q -m gpu -x --timeout=300 -p no:cacheprovider > "gpurun_out/diag_${name}.log" 2>&1
+  timeout 600 python -m pytest "$f" -q -m gpu --timeout=300 -s -p no:cacheprovider > "gpurun_out/diag_${name}.log" 2>&1
   echo "exit $?" | tee -a gpurun_out/diag_summary.txt
   tail -n 25 "gpurun_out/diag_${name}.log" | tee -a gpurun_out/diag_summary.txt
 done

@@ -30,8 +30,8 @@ def test_gemm_f32_epilogue(M, N, K):
     bias = _rand((N,), 3, 1.0, torch.float32)
     got = G.gemm(A, W, _lib.EPI_F32, bias=bias)
     want = A.float() @ W.float().T + bias
-    assert G.rel_err(got, want) < 2e-6
-    assert (got - want).abs().max() < 1e-3 * want.abs().max()
+    assert G.rel_err(got, want) < 1e-5          # fp32 accumulation order only
+    assert (got - want).abs().max() < 1e-4 * want.abs().max()
 
 
 @pytest.mark.parametrize("act", [0, 1, 2, 3])
@@ -59,7 +59,7 @@ def test_gemm_residual_epilogue(use_ls):
     G.gemm(A, W, _lib.EPI_RESID_F32, bias=bias, colscale=ls, C_inout=x)
     delta = A.float() @ W.float().T + bias
     want = x0 + (delta * ls if use_ls else delta)
-    assert G.rel_err(x, want) < 2e-6
+    assert G.rel_err(x, want) < 1e-5
 
 
 def test_gemm_rejects_bad_shapes():
