@@ -22,7 +22,7 @@ struct AttnArgs {
   int T;        // tokens per image
   int H;        // heads
   int nb;       // ceil(T / 128)
-  int last_w;   // width of the last KV block, multiple of 16
+  int last_w;   // width of the last KV block, multiple of 32
   float scale;  // head_dim^-0.5
   __nv_bfloat16* out;  // [N*T, H*64]
 };
@@ -169,16 +169,20 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnAr
         const uint32_t sb = sc & 1;
         mbar_wait(&s_full[sb], (sc >> 1) & 1);
         tc_fence_after();
-        const int width = (j == nb - 1) ? p.last_w : 128;
+        const int nch = ((j == nb - 1) ? p.last_w : 128) >> 5;  // 32-column chunks
         const int valid = min(128, p.T - j * 128);
         const uint32_t ts = tmem_S + lane_sel + sb * 128;
-        for (int c = 0; c < width; c += 16) {
-          uint32_t v[16];
-          tmem_ld_32x32b_x16(ts + c, v);
-          tmem_ld_wait();
+        uint32_t buf[2][32];
+        tmem_ld_32x32b_x32(ts, buf[0]);
 #pragma unroll
-          for (int e = 0; e < 16; ++e)
-            if (c + e < valid) m = fmaxf(m, __uint_as_float(v[e]));
+        for (int c = 0; c < 4; ++c) {
+          if (c < nch) {  // warp-uniform
+            tmem_ld_wait_dep(buf[c & 1]);
+            if (c + 1 < nch) tmem_ld_32x32b_x32(ts + (c + 1) * 32, buf[(c + 1) & 1]);  // in flight during the max
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (c * 32 + e < valid) m = fmaxf(m, __uint_as_float(buf[c & 1][e]));
+          }
         }
         tc_fence_before();
         __syncwarp();
@@ -192,23 +196,25 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnAr
         mbar_wait(&s_full[sb], (sc >> 1) & 1);
         tc_fence_after();
         const int width = (j == nb - 1) ? p.last_w : 128;
+        const int nch = width >> 5;
         const int valid = min(128, p.T - j * 128);
         const uint32_t ts = tmem_S + lane_sel + sb * 128;
         uint32_t pk[64];  // the whole P row of this block, packed bf16x2
+        uint32_t buf[2][32];
+        tmem_ld_32x32b_x32(ts, buf[0]);
 #pragma unroll
-        for (int c = 0; c < 128; c += 16) {
-          if (c < width) {  // warp-uniform
-            uint32_t v[16];
-            tmem_ld_32x32b_x16(ts + c, v);
-            tmem_ld_wait();
+        for (int c = 0; c < 4; ++c) {
+          if (c < nch) {  // warp-uniform
+            tmem_ld_wait_dep(buf[c & 1]);
+            if (c + 1 < nch) tmem_ld_32x32b_x32(ts + (c + 1) * 32, buf[(c + 1) & 1]);  // overlaps the exps below
 #pragma unroll
-            for (int i = 0; i < 16; i += 2) {
-              float e0 = ex2_approx(fmaf(__uint_as_float(v[i]), c1, -mc));
-              float e1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), c1, -mc));
-              e0 = (c + i < valid) ? e0 : 0.f;
-              e1 = (c + i + 1 < valid) ? e1 : 0.f;
+            for (int i = 0; i < 32; i += 2) {
+              float e0 = ex2_approx(fmaf(__uint_as_float(buf[c & 1][i]), c1, -mc));
+              float e1 = ex2_approx(fmaf(__uint_as_float(buf[c & 1][i + 1]), c1, -mc));
+              e0 = (c * 32 + i < valid) ? e0 : 0.f;
+              e1 = (c * 32 + i + 1 < valid) ? e1 : 0.f;
               l += e0 + e1;
-              pk[(c + i) >> 1] = pack_bf16x2(e0, e1);
+              pk[(c * 32 + i) >> 1] = pack_bf16x2(e0, e1);
             }
           }
         }

@@ -273,7 +273,7 @@ int launch_attention(const void* qkv, void* out, int n_img, int T, int H, int im
   if (nb > lovr::kAttnMaxBlocks) return fail(LOVR_E_UNSUPPORTED, "attention: T=%d > 640 tokens", T);
   const int rem = T - 128 * (nb - 1);
   lovr::AttnArgs a{};
-  a.T = T; a.H = H; a.nb = nb; a.last_w = (rem + 15) / 16 * 16; a.scale = 0.125f;
+  a.T = T; a.H = H; a.nb = nb; a.last_w = (rem + 31) / 32 * 32; a.scale = 0.125f;
   a.out = static_cast<__nv_bfloat16*>(out);
   CUtensorMap tq;
   int rc;
