@@ -129,6 +129,30 @@ size_t lovr_a_score_workspace_bytes(int32_t dtype, int64_t n_pairs, int32_t x, i
 int lovr_a_score_maxcos(const void* other, const void* ref, int32_t dtype, int64_t n_pairs, int32_t x, int32_t y,
                         int32_t D, float* pair_score, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * C score (replaces C_score/pck_train.py:24-29 normalize_feats + C_score/utils/utils_correspondence.py:345-382
+ * calculate_keypoint_transformation / :297-337 get_flow / :234-256 soft_argmax, and pck_train.py:150-163 PCK).
+ * desc1/desc2 [n_pairs, P*P, D] UN-normalised patch descriptors (bf16 or fp32), rows in row-major patch order.
+ *   lovr_c_score_flow:      the dense path — normalise, P^2 x P^2 similarity on tcgen05 (fp32 inputs are split into
+ *                           bf16 hi/lo terms: |error| ~1e-6), row argmax, windowed soft-argmax over every source row.
+ *                           flow [n_pairs, P*P, 2] = (x, y) in patch units == get_flow(...).reshape(-1, 2);
+ *                           argmax [n_pairs, P*P] (may be NULL) == sim.argmax(-1).  soft=0 gives the argmax coordinates.
+ *   lovr_c_score_keypoints: what the reference's callers consume — only the K source-keypoint rows
+ *                           (patch_idx [n_pairs, K] from kpts_to_patch_idx :384-389), similarity in plain fp32;
+ *                           kps_out [n_pairs, K, 2] = (x, y) pixels = clamp(flow)*stride + stride//2, stride=anno/P.
+ *   lovr_pck:               out [n_pairs, 4] = PCK@0.10, @0.05, @0.01 over visible keypoints, #visible.
+ * Workspace: lovr_c_score_workspace_bytes(dtype, n_pairs, P, D, K) with K=0 for the dense path.
+ * ------------------------------------------------------------------------------------------------- */
+size_t lovr_c_score_workspace_bytes(int32_t dtype, int64_t n_pairs, int32_t P, int32_t D, int32_t K);
+int lovr_c_score_flow(const void* desc1, const void* desc2, int32_t dtype, int64_t n_pairs, int32_t P, int32_t D,
+                      int32_t window, int32_t soft, float* flow, int32_t* argmax, void* workspace,
+                      size_t workspace_bytes, void* stream);
+int lovr_c_score_keypoints(const void* desc1, const void* desc2, int32_t dtype, int64_t n_pairs, int32_t P, int32_t D,
+                           const int32_t* patch_idx, int32_t K, int32_t window, int32_t soft, float anno_size,
+                           float* kps_out, void* workspace, size_t workspace_bytes, void* stream);
+int lovr_pck(const float* pred, const float* gt, const uint8_t* visible, const float* thresholds, int64_t n_pairs,
+             int32_t K, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,6 +20,7 @@ EXPORTS = [
     "lovr_tower_workspace_bytes", "lovr_tower_create", "lovr_tower_destroy", "lovr_tower_forward",
     "lovr_gemm_bf16", "lovr_layernorm_bf16", "lovr_attention", "lovr_im2col",
     "lovr_a_score_workspace_bytes", "lovr_a_score_maxcos",
+    "lovr_c_score_workspace_bytes", "lovr_c_score_flow", "lovr_c_score_keypoints", "lovr_pck",
 ]
 
 
@@ -84,6 +85,14 @@ def lib():
     L.lovr_a_score_workspace_bytes.argtypes = [i32, i64, i32, i32, i32]
     L.lovr_a_score_maxcos.restype = C.c_int
     L.lovr_a_score_maxcos.argtypes = [vp, vp, i32, i64, i32, i32, i32, vp, vp, sz, vp]
+    L.lovr_c_score_workspace_bytes.restype = sz
+    L.lovr_c_score_workspace_bytes.argtypes = [i32, i64, i32, i32, i32]
+    L.lovr_c_score_flow.restype = C.c_int
+    L.lovr_c_score_flow.argtypes = [vp, vp, i32, i64, i32, i32, i32, i32, vp, vp, vp, sz, vp]
+    L.lovr_c_score_keypoints.restype = C.c_int
+    L.lovr_c_score_keypoints.argtypes = [vp, vp, i32, i64, i32, i32, vp, i32, i32, i32, f32, vp, vp, sz, vp]
+    L.lovr_pck.restype = C.c_int
+    L.lovr_pck.argtypes = [vp, vp, vp, vp, i64, i32, vp, vp]
     _lib = L
     return L
 

@@ -1,0 +1,159 @@
+"""C score on the device (reference: C_score/pck_train.py + C_score/utils/utils_correspondence.py).
+
+Reference call chain per image pair (pck_train.py:96-163):
+    desc = torch.load(<img>_<MODEL>.pt) [1,C,h,w] -> [1,P*P,C]          prepare_feature_paths_and_load :31-44
+    desc = normalize_feats(desc)                                           :24-29
+    idx  = kpts_to_patch_idx(args, img1_kps, P)                            utils_correspondence.py:384-389
+    kps  = calculate_keypoint_transformation(args, d1, d2, idx, P)         :345-382  (sim -> get_flow -> index -> pixels)
+    pck  = mean(||kps - gt|| < alpha * bbox)  alpha in {.1,.05,.01}        pck_train.py:150-163
+    C    = np.average(per-category mean PCK@0.10, weights=#pairs)          utils/logger.py:61-65
+
+Here `keypoint_transformation` (only the K keypoint rows, plain fp32 — what the callers consume) and `get_flow`
+(the dense P^2 x P^2 path on tcgen05) take UN-normalised descriptors; normalisation is fused.
+"""
+import ctypes as C
+from collections import defaultdict
+
+import numpy as np
+import torch
+
+from . import _lib
+
+ANNO_SIZE = 840
+_DENSE_PAIRS_PER_CALL = 8
+
+
+def desc_from_feature_map(fmap):
+    """pck_train.py:38-39 with the identity aggregation net: [1,C,h,w] -> [1, h*w, C]."""
+    return fmap.reshape(1, 1, fmap.shape[1], -1).permute(0, 1, 3, 2)[0]
+
+
+def concat_two_models(desc_a, desc_b, eps=1e-10):
+    """pck_train_two.py:24-35 — normalise each model's descriptors, concatenate channels (the fused kernels then
+    renormalise).  Tiny per-token arithmetic on [B,P*P,C]; kept in torch as data preparation."""
+    na = desc_a / (torch.linalg.norm(desc_a, dim=-1, keepdim=True) + eps)
+    nb = desc_b / (torch.linalg.norm(desc_b, dim=-1, keepdim=True) + eps)
+    return torch.cat([na, nb], dim=-1)
+
+
+def kpts_to_patch_idx(kps, num_patches, anno_size=ANNO_SIZE):
+    """utils_correspondence.py:384-389 (host integer arithmetic, numpy like the reference)."""
+    k = kps.detach().cpu()
+    y, x = k[..., 1].numpy(), k[..., 0].numpy()
+    yp = (num_patches / anno_size * y).astype(np.int32)
+    xp = (num_patches / anno_size * x).astype(np.int32)
+    return num_patches * yp + xp
+
+
+def _prep(d1, d2, mult):
+    if d1.dim() == 2:
+        d1, d2 = d1[None], d2[None]
+    if d1.shape != d2.shape or d1.dim() != 3:
+        raise ValueError(f"expected two [B,P*P,D] tensors, got {tuple(d1.shape)} and {tuple(d2.shape)}")
+    if not d1.is_cuda:
+        raise _lib.LovrError("C-score kernels need CUDA tensors: this package has no CPU path")
+    if d1.dtype not in (torch.float32, torch.bfloat16):
+        d1, d2 = d1.float(), d2.float()
+    d2 = d2.to(d1.dtype)
+    D = d1.shape[-1]
+    if D % mult:
+        pad = mult - D % mult                   # zero channels change neither dot products nor norms
+        d1, d2 = torch.nn.functional.pad(d1, (0, pad)), torch.nn.functional.pad(d2, (0, pad))
+    P = int(round(d1.shape[1] ** 0.5))
+    if P * P != d1.shape[1]:
+        raise ValueError(f"{d1.shape[1]} patches is not a square grid")
+    return d1.contiguous(), d2.contiguous(), P
+
+
+def _workspace(nbytes, device):
+    ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+    return ws, C.c_void_p((ws.data_ptr() + 1023) // 1024 * 1024)
+
+
+def get_flow(desc1, desc2, window=5, soft=True, return_argmax=False):
+    """Dense correspondence for every source patch: == utils_correspondence.get_flow(sim, window, P).reshape(-1,2)
+    per pair, with sim = n(desc1) @ n(desc2)^T.  -> flow [B,P*P,2] (x,y in patch units) (, argmax [B,P*P])."""
+    d1, d2, P = _prep(desc1, desc2, 64)
+    B, PP, D = d1.shape
+    L = _lib.lib()
+    dt = _lib.torch_dtype_code(d1.dtype)
+    flow = torch.empty(B, PP, 2, dtype=torch.float32, device=d1.device)
+    amax = torch.empty(B, PP, dtype=torch.int32, device=d1.device)
+    step = min(B, _DENSE_PAIRS_PER_CALL)
+    nbytes = L.lovr_c_score_workspace_bytes(dt, step, P, D, 0)
+    ws, base = _workspace(nbytes, d1.device)
+    with torch.cuda.device(d1.device):
+        st = _lib.stream_ptr(d1.device)
+        for s in range(0, B, step):
+            e = min(B, s + step)
+            _lib.check(L.lovr_c_score_flow(_lib.ptr(d1[s:e]), _lib.ptr(d2[s:e]), dt, e - s, P, D, window, int(soft),
+                                           _lib.ptr(flow[s:e]), _lib.ptr(amax[s:e]), base, nbytes, st),
+                       "lovr_c_score_flow")
+    return (flow, amax) if return_argmax else flow
+
+
+def keypoint_transformation(desc1, desc2, patch_idx, soft=True, window=5, anno_size=ANNO_SIZE):
+    """== calculate_keypoint_transformation(args(SOFT_EVAL=soft, SOFT_EVAL_WINDOW=window, ANNO_SIZE), n(d1), n(d2),
+    patch_idx, P) for a batch of pairs: desc [B,P*P,D], patch_idx [B,K] int -> [B,K,2] (x,y) pixels."""
+    d1, d2, P = _prep(desc1, desc2, 32)
+    B, PP, D = d1.shape
+    idx = torch.as_tensor(np.asarray(patch_idx), dtype=torch.int32).reshape(B, -1).to(d1.device).contiguous()
+    K = idx.shape[1]
+    if idx.numel() and (int(idx.min()) < 0 or int(idx.max()) >= PP):
+        raise IndexError(f"index out of bounds for dimension 0 with size {PP}")
+    L = _lib.lib()
+    dt = _lib.torch_dtype_code(d1.dtype)
+    out = torch.empty(B, K, 2, dtype=torch.float32, device=d1.device)
+    nbytes = L.lovr_c_score_workspace_bytes(dt, B, P, D, K)
+    ws, base = _workspace(nbytes, d1.device)
+    with torch.cuda.device(d1.device):
+        _lib.check(L.lovr_c_score_keypoints(_lib.ptr(d1), _lib.ptr(d2), dt, B, P, D, _lib.ptr(idx), K, window, int(soft),
+                                            float(anno_size), _lib.ptr(out), base, nbytes, _lib.stream_ptr(d1.device)),
+                   "lovr_c_score_keypoints")
+    return out
+
+
+def pck_per_pair(pred, gt, visible, thresholds):
+    """pck_train.py:150-163 for a batch: pred/gt [B,K,2] (x,y), visible [B,K] bool, thresholds [B] (bbox size, or
+    ANNO_SIZE when the dataset has none) -> [B,4] = PCK@.10, @.05, @.01, #visible."""
+    B, K, _ = pred.shape
+    dev = pred.device
+    out = torch.empty(B, 4, dtype=torch.float32, device=dev)
+    vis = visible.to(dev, torch.uint8).contiguous()
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().lovr_pck(_lib.ptr(pred.float().contiguous()), _lib.ptr(gt.to(dev).float().contiguous()),
+                                       _lib.ptr(vis), _lib.ptr(thresholds.to(dev).float().contiguous()), B, K,
+                                       _lib.ptr(out), _lib.stream_ptr(dev)), "lovr_pck")
+    return out
+
+
+def category_sums(pck, categories, n_categories):
+    """Per-rank partial sums for the data-parallel reduction: [n_categories, 4] =
+    sum PCK@.10, @.05, @.01 over this rank's pairs and #pairs.  One all-reduce(sum) of this tensor, then
+    `weighted_c_score`."""
+    sums = torch.zeros(n_categories, 4, dtype=torch.float64, device=pck.device)
+    cat = torch.as_tensor(categories, device=pck.device, dtype=torch.long)
+    sums[:, :3].index_add_(0, cat, pck[:, :3].double())
+    sums[:, 3].index_add_(0, cat, torch.ones(len(cat), dtype=torch.float64, device=pck.device))
+    return sums
+
+
+def weighted_c_score(sums):
+    """compute_pck's per-category image means (pck_train.py:204-209) then np.average(..., weights=#pairs)
+    (utils/logger.py:61-65).  -> (PCK@0.10, @0.05, @0.01); the first one is the paper's C score (`corres`)."""
+    s = sums.detach().cpu().numpy()
+    n = s[:, 3]
+    keep = n > 0
+    means = s[keep, :3] / n[keep, None]
+    return tuple(float(np.average(means[:, i], weights=n[keep])) for i in range(3))
+
+
+def c_score(desc1, desc2, kps1, kps2, thresholds, categories, n_categories, soft=True, window=5, anno_size=ANNO_SIZE):
+    """End to end for a batch of pairs on this rank: descriptors [B,P*P,D], kps [B,K,3] (x,y,visible).
+    Returns (category partial sums [n_categories,4], predicted kps [B,K,2])."""
+    P = int(round(desc1.shape[1] ** 0.5))
+    idx = kpts_to_patch_idx(kps1.reshape(-1, 3), P, anno_size).reshape(kps1.shape[0], -1)
+    pred = keypoint_transformation(desc1, desc2, idx, soft, window, anno_size)
+    vis = (kps1[..., 2] * kps2[..., 2]) > 0                      # pck_train.py:131
+    pck = pck_per_pair(pred, kps2[..., :2], vis, thresholds)
+    return category_sums(pck, categories, n_categories), pred

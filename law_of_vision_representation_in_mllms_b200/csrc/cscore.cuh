@@ -1,0 +1,194 @@
+// C-score kernels (reference: C_score/utils/utils_correspondence.py:226-277,297-337,345-382 and
+// C_score/pck_train.py:142-163): windowed soft-argmax over similarity rows, the keypoint-rows similarity
+// (only the K source-keypoint rows of the P^2 x P^2 matrix are consumed by the reference's callers), and PCK.
+#pragma once
+#include "ptx.cuh"
+
+namespace lovr {
+
+constexpr int kMaxGrid = 64;   // P <= 64
+constexpr int kMaxKps = 32;    // keypoints per pair (SPair-71k: <= 30)
+
+// One warp per similarity row.  sim row r: P*P fp32 values (targets, row-major ty*P+tx), row stride ld.
+//   mode 0: hard  — flow = (argmax % P, argmax / P)                                   (:372-373)
+//   mode 1: soft  — window > 0: entries outside the clamped (2W+1)^2 window around the row argmax are set to
+//                   ZERO (not -inf) before softmax((s - max)/beta) over ALL P*P targets (:305-327, :226-232);
+//                   the P*P - |window| zero entries are folded in analytically: each contributes exp(-M/beta)
+//                   to the denominator and exp(-M/beta)*lin(.) to the numerators.
+//                   window == 0: plain soft-argmax over the whole row.
+// flow[r] = ((E[x]+1)(P-1)/2, (E[y]+1)(P-1)/2) in patch units (:239-255, :264-265), x,y on linspace(-1,1,P).
+// If stride > 0 the row is a keypoint row and out = clamp(flow,0,P-1)*stride + floor(stride/2)   (:369,:376-377).
+__global__ void flow_rows_kernel(const float* __restrict__ sim, size_t ld, size_t rows, int P, int window, float beta,
+                                 int mode, float stride, float* __restrict__ flow, int* __restrict__ argmax_out) {
+  __shared__ float lin[kMaxGrid];
+  if (threadIdx.x < P) lin[threadIdx.x] = static_cast<float>(-1.0 + threadIdx.x * (2.0 / (P - 1)));
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const size_t row = blockIdx.x * static_cast<size_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* s = sim + row * ld;
+  const int PP = P * P;
+  // ---- row argmax, first index on ties (torch.argmax)
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int t = lane; t < PP; t += 32) {
+    const float v = __ldg(s + t);
+    if (v > bv) { bv = v; bi = t; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  if (argmax_out != nullptr && lane == 0) argmax_out[row] = bi;
+  float fx, fy;
+  if (mode == 0) {
+    fx = static_cast<float>(bi % P);
+    fy = static_cast<float>(bi / P);
+  } else {
+    int y0 = 0, y1 = P - 1, x0 = 0, x1 = P - 1;
+    if (window > 0) {
+      const int my = bi / P, mx = bi % P;
+      y0 = max(my - window, 0); y1 = min(my + window, P - 1);
+      x0 = max(mx - window, 0); x1 = min(mx + window, P - 1);
+    }
+    const int wx = x1 - x0 + 1;
+    const int nwin = wx * (y1 - y0 + 1);
+    const int tail = PP - nwin;
+    float M = -INFINITY;
+    for (int i = lane; i < nwin; i += 32) M = fmaxf(M, __ldg(s + (y0 + i / wx) * P + x0 + i % wx));
+    M = warp_max(M);
+    if (tail > 0) M = fmaxf(M, 0.f);
+    float sw = 0.f, sx = 0.f, sy = 0.f, lx = 0.f, ly = 0.f;
+    for (int i = lane; i < nwin; i += 32) {
+      const int y = y0 + i / wx, x = x0 + i % wx;
+      const float w = expf((__ldg(s + y * P + x) - M) / beta);
+      sw += w;
+      sx += w * lin[x];
+      sy += w * lin[y];
+      lx += lin[x];
+      ly += lin[y];
+    }
+    sw = warp_sum(sw); sx = warp_sum(sx); sy = warp_sum(sy); lx = warp_sum(lx); ly = warp_sum(ly);
+    if (tail > 0) {
+      // sum of lin over ALL positions is 0 by symmetry, so the masked-out positions sum to -(window sum)
+      const float wt = expf((0.f - M) / beta);
+      sw += wt * static_cast<float>(tail);
+      sx -= wt * lx;
+      sy -= wt * ly;
+    }
+    fx = (sx / sw + 1.f) * (P - 1) / 2.0f;
+    fy = (sy / sw + 1.f) * (P - 1) / 2.0f;
+  }
+  if (lane == 0) {
+    if (stride > 0.f) {
+      const float half = floorf(stride / 2.0f);  // python `anno_stride // 2` on floats
+      fx = fminf(fmaxf(fx, 0.f), static_cast<float>(P - 1)) * stride + half;
+      fy = fminf(fmaxf(fy, 0.f), static_cast<float>(P - 1)) * stride + half;
+    }
+    flow[row * 2 + 0] = fx;
+    flow[row * 2 + 1] = fy;
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+// Keypoint rows of the similarity matrix in plain fp32 (the arithmetic the reference's fp32 matmul performs):
+//   out[b, k, t] = n(d1[b, idx[b,k], :]) . n(d2[b, t, :]),   n(x) = x / (||x|| + 1e-10)   (pck_train.py:24-29)
+// grid (ceil(PP / rows_per_block), n_pairs); smem: K normalised source rows (K*D floats).
+template <typename T>
+__global__ void kp_sim_rows_kernel(const T* __restrict__ d1, const T* __restrict__ d2, const int* __restrict__ idx,
+                                   int K, int PP, int D, int rows_per_block, float* __restrict__ out) {
+  extern __shared__ float s1[];  // [K][D]
+  __shared__ float s_inv[kMaxKps];
+  const int b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const T* d1b = d1 + static_cast<size_t>(b) * PP * D;
+  const T* d2b = d2 + static_cast<size_t>(b) * PP * D;
+  for (int k = warp; k < K; k += nwarps) {
+    const int r = idx[static_cast<size_t>(b) * K + k];
+    float ss = 0.f;
+    for (int e = lane; e < D; e += 32) {
+      const float v = to_f32<T>(d1b[static_cast<size_t>(r) * D + e]);
+      s1[k * D + e] = v;
+      ss += v * v;
+    }
+    ss = warp_sum(ss);
+    if (lane == 0) s_inv[k] = 1.0f / (sqrtf(ss) + 1e-10f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * D; i += blockDim.x) s1[i] *= s_inv[i / D];
+  __syncthreads();
+  const int t0 = blockIdx.x * rows_per_block;
+  const int t1 = min(PP, t0 + rows_per_block);
+  for (int t = t0 + warp; t < t1; t += nwarps) {
+    float dots[kMaxKps];
+#pragma unroll
+    for (int k = 0; k < kMaxKps; ++k) dots[k] = 0.f;
+    float ss = 0.f;
+    for (int c = 0; c < D; c += 1024) {
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int e = c + lane + 32 * i;
+        v[i] = (e < D) ? to_f32<T>(d2b[static_cast<size_t>(t) * D + e]) : 0.f;
+        ss += v[i] * v[i];
+      }
+#pragma unroll
+      for (int k = 0; k < kMaxKps; ++k) {
+        if (k < K) {
+          float a = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int e = c + lane + 32 * i;
+            if (e < D) a += v[i] * s1[k * D + e];
+          }
+          dots[k] += a;
+        }
+      }
+    }
+    ss = warp_sum(ss);
+    const float inv2 = 1.0f / (sqrtf(ss) + 1e-10f);
+#pragma unroll
+    for (int k = 0; k < kMaxKps; ++k) {
+      if (k < K) {
+        const float d = warp_sum(dots[k]);
+        if (lane == 0) out[(static_cast<size_t>(b) * K + k) * PP + t] = d * inv2;
+      }
+    }
+  }
+}
+
+// Per-pair PCK (pck_train.py:150-163): fraction of visible keypoints with ||pred-gt|| < alpha*thr,
+// alpha in {0.1, 0.05, 0.01}.  out[b] = {pck@.1, pck@.05, pck@.01, #visible}.
+__global__ void pck_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
+                           const unsigned char* __restrict__ vis, const float* __restrict__ thr, int n, int K,
+                           float* __restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n) return;
+  int nv = 0, c1 = 0, c2 = 0, c3 = 0;
+  const float t = thr[b];
+  for (int k = 0; k < K; ++k) {
+    if (!vis[static_cast<size_t>(b) * K + k]) continue;
+    const size_t o = (static_cast<size_t>(b) * K + k) * 2;
+    const float dx = gt[o] - pred[o], dy = gt[o + 1] - pred[o + 1];
+    const float err = sqrtf(dx * dx + dy * dy);
+    ++nv;
+    c1 += err < 0.1f * t;
+    c2 += err < 0.05f * t;
+    c3 += err < 0.01f * t;
+  }
+  const float d = nv > 0 ? static_cast<float>(nv) : 1.f;
+  out[b * 4 + 0] = c1 / d;
+  out[b * 4 + 1] = c2 / d;
+  out[b * 4 + 2] = c3 / d;
+  out[b * 4 + 3] = static_cast<float>(nv);
+}
+
+}  // namespace lovr

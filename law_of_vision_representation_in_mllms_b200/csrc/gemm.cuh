@@ -42,6 +42,7 @@ struct GemmArgs {
   const float* rowscale;  // EPI_ROWMAX: [batch, M] 1/||other||
   float* rowmax;          // EPI_ROWMAX: [batch, M]
   int n_valid;            // EPI_ROWMAX: real number of columns (<= N)
+  int scale_ld;           // EPI_F32 with colscale/rowscale: per-batch stride of both scale vectors (padded)
 };
 
 template <int BN>
@@ -260,6 +261,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               const float bb[4] = {b0.x, b0.y, b0.z, b0.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) v[e] = __uint_as_float(r0[j * 4 + e]) + bb[e];
+              if (p.colscale) {  // similarity GEMMs: C = rowscale[b,row] * colscale[b,col] * acc (padded to BN)
+                const float4 s0 =
+                    __ldg(reinterpret_cast<const float4*>(p.colscale + static_cast<size_t>(b) * p.scale_ld + col0 + j * 4));
+                const float rs = __ldg(p.rowscale + static_cast<size_t>(b) * p.scale_ld + min(row0 + lane, p.M - 1));
+                v[0] *= s0.x * rs;
+                v[1] *= s0.y * rs;
+                v[2] *= s0.z * rs;
+                v[3] *= s0.w * rs;
+              }
               st_shared_v4(buf_row + ((j ^ row_sw) << 4), __float_as_uint(v[0]), __float_as_uint(v[1]),
                            __float_as_uint(v[2]), __float_as_uint(v[3]));
             }

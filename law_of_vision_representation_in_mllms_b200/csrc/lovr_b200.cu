@@ -15,6 +15,7 @@
 
 #include "attention.cuh"
 #include "attention_simt.cuh"
+#include "cscore.cuh"
 #include "gemm.cuh"
 #include "rowwise.cuh"
 #include "scores.cuh"
@@ -226,7 +227,8 @@ int dense_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, 
   }
   lovr::GemmArgs g{};
   g.M = M; g.N = N; g.K = K; g.batch = 1; g.n_inner = 1;
-  g.bias = bias; g.colscale = colscale; g.rowscale = nullptr; g.rowmax = nullptr; g.n_valid = N;
+  g.bias = bias; g.colscale = colscale; g.rowscale = nullptr; g.rowmax = nullptr; g.n_valid = N; g.scale_ld = 0;
+  if (epi == lovr::EPI_F32) g.colscale = nullptr;  // (similarity scaling is only used by the C-score path)
   return launch_gemm(kDenseBN, epi, act, ta, tb, tc, g, s);
 }
 
@@ -608,6 +610,155 @@ int lovr_a_score_maxcos(const void* other, const void* ref, int32_t dtype, int64
   if ((rc = launch_gemm(bn, EPI_ROWMAX, ACT_NONE, ta, tb, ta /*unused*/, g, s))) return rc;
   pair_mean_kernel<<<static_cast<unsigned>(n_pairs), 256, 0, s>>>(rowmax, pair_score, x);
   LAUNCH_CHECK("pair_mean_kernel");
+  return 0;
+}
+
+// ====================================================================================== C score
+namespace {
+struct CScoreLayout {
+  size_t inv1, inv2, sim, split1, split2, total;
+  int scale_ld, sim_ld;
+};
+CScoreLayout c_layout(int dtype, int64_t n, int P, int D) {
+  CScoreLayout l{};
+  const int PP = P * P;
+  l.scale_ld = (PP + 255) / 256 * 256 + 256;  // float4 epilogue loads may run past P*P inside the last N tile
+  l.sim_ld = (PP + 3) / 4 * 4;
+  size_t off = 0;
+  l.inv1 = off; off += align_up(static_cast<size_t>(n) * l.scale_ld * 4, 1024);
+  l.inv2 = off; off += align_up(static_cast<size_t>(n) * l.scale_ld * 4, 1024);
+  l.sim = off; off += align_up(static_cast<size_t>(n) * PP * l.sim_ld * 4, 1024);
+  if (dtype == LOVR_DT_F32) {
+    l.split1 = off; off += align_up(static_cast<size_t>(n) * PP * 3 * D * 2, 1024);
+    l.split2 = off; off += align_up(static_cast<size_t>(n) * PP * 3 * D * 2, 1024);
+  }
+  l.total = off;
+  return l;
+}
+int check_c_args(const void* d1, const void* d2, int dtype, int64_t n, int P, int D) {
+  if (!d1 || !d2) return fail(LOVR_E_ARG, "c_score: null pointer");
+  if (dtype != LOVR_DT_BF16 && dtype != LOVR_DT_F32) return fail(LOVR_E_UNSUPPORTED, "c_score: dtype %d (bf16 or fp32)", dtype);
+  if (P < 2 || P > lovr::kMaxGrid) return fail(LOVR_E_UNSUPPORTED, "c_score: grid side P=%d outside [2,%d]", P, lovr::kMaxGrid);
+  if (n <= 0 || D <= 0) return fail(LOVR_E_ARG, "c_score: sizes must be positive");
+  return 0;
+}
+int launch_flow_rows(const float* sim, size_t ld, size_t rows, int P, int window, int soft, float stride, float* flow,
+                     int* argmax, cudaStream_t s) {
+  const int wpb = 8;
+  lovr::flow_rows_kernel<<<static_cast<unsigned>((rows + wpb - 1) / wpb), wpb * 32, 0, s>>>(
+      sim, ld, rows, P, window, 0.02f, soft ? 1 : 0, stride, flow, argmax);
+  LAUNCH_CHECK("flow_rows_kernel");
+  return 0;
+}
+}  // namespace
+
+size_t lovr_c_score_workspace_bytes(int32_t dtype, int64_t n_pairs, int32_t P, int32_t D, int32_t K) {
+  if (K > 0) return align_up(static_cast<size_t>(n_pairs) * K * P * P * 4, 1024);  // keypoint rows only
+  return c_layout(dtype, n_pairs, P, D).total;
+}
+
+int lovr_c_score_flow(const void* desc1, const void* desc2, int32_t dtype, int64_t n_pairs, int32_t P, int32_t D,
+                      int32_t window, int32_t soft, float* flow, int32_t* argmax, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  using namespace lovr;
+  if (int rc = require_device()) return rc;
+  if (int rc = check_c_args(desc1, desc2, dtype, n_pairs, P, D)) return rc;
+  if (!flow || !workspace) return fail(LOVR_E_ARG, "c_score_flow: null pointer");
+  if (D % 64) return fail(LOVR_E_ARG, "c_score_flow: D=%d must be a multiple of 64 (pad channels with zeros)", D);
+  const CScoreLayout l = c_layout(dtype, n_pairs, P, D);
+  if (workspace_bytes < l.total) return fail(LOVR_E_NOMEM, "c_score workspace %zu < %zu", workspace_bytes, l.total);
+  if (reinterpret_cast<uintptr_t>(workspace) & 1023) return fail(LOVR_E_ARG, "workspace must be 1024-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  auto base = static_cast<uint8_t*>(workspace);
+  float* inv1 = reinterpret_cast<float*>(base + l.inv1);
+  float* inv2 = reinterpret_cast<float*>(base + l.inv2);
+  float* sim = reinterpret_cast<float*>(base + l.sim);
+  const int PP = P * P;
+  const size_t rows = static_cast<size_t>(n_pairs) * PP;
+  const int wpb = 8;
+  const unsigned grid = static_cast<unsigned>((rows + wpb - 1) / wpb);
+  // padded tails of the scale vectors are read by the last N tile's float4 loads: keep them finite
+  CUDA_TRY(cudaMemsetAsync(inv1, 0, static_cast<size_t>(n_pairs) * l.scale_ld * 4, s));
+  CUDA_TRY(cudaMemsetAsync(inv2, 0, static_cast<size_t>(n_pairs) * l.scale_ld * 4, s));
+  const void* a_ptr = desc1;
+  const void* b_ptr = desc2;
+  int K = D;
+  if (dtype == LOVR_DT_BF16) {
+    rownorm_inv_bf16_kernel<<<grid, wpb * 32, 0, s>>>(static_cast<const __nv_bfloat16*>(desc1), inv1, rows, D, 1, PP, l.scale_ld);
+    LAUNCH_CHECK("rownorm_inv_bf16_kernel");
+    rownorm_inv_bf16_kernel<<<grid, wpb * 32, 0, s>>>(static_cast<const __nv_bfloat16*>(desc2), inv2, rows, D, 1, PP, l.scale_ld);
+    LAUNCH_CHECK("rownorm_inv_bf16_kernel");
+  } else {
+    auto s1 = reinterpret_cast<__nv_bfloat16*>(base + l.split1);
+    auto s2 = reinterpret_cast<__nv_bfloat16*>(base + l.split2);
+    split3_kernel<<<grid, wpb * 32, 0, s>>>(static_cast<const float*>(desc1), s1, inv1, rows, D, 0, 1, PP, l.scale_ld);
+    LAUNCH_CHECK("split3_kernel");
+    split3_kernel<<<grid, wpb * 32, 0, s>>>(static_cast<const float*>(desc2), s2, inv2, rows, D, 1, 1, PP, l.scale_ld);
+    LAUNCH_CHECK("split3_kernel");
+    a_ptr = s1;
+    b_ptr = s2;
+    K = 3 * D;
+  }
+  CUtensorMap ta, tb, tc;
+  int rc;
+  if ((rc = make_tmap(&ta, a_ptr, 2, K, PP, n_pairs, K, static_cast<uint64_t>(K) * PP, 64, kBM))) return rc;
+  if ((rc = make_tmap(&tb, b_ptr, 2, K, PP, n_pairs, K, static_cast<uint64_t>(K) * PP, 64, 256))) return rc;
+  if ((rc = make_tmap(&tc, sim, 4, PP, PP, n_pairs, l.sim_ld, static_cast<uint64_t>(l.sim_ld) * PP, 32, 32))) return rc;
+  GemmArgs g{};
+  g.M = PP; g.N = PP; g.K = K; g.batch = static_cast<int>(n_pairs); g.n_inner = 1;
+  g.bias = nullptr; g.colscale = inv2; g.rowscale = inv1; g.rowmax = nullptr; g.n_valid = PP; g.scale_ld = l.scale_ld;
+  if ((rc = launch_gemm(256, EPI_F32, ACT_NONE, ta, tb, tc, g, s))) return rc;
+  return launch_flow_rows(sim, l.sim_ld, rows, P, window, soft, 0.f, flow, argmax, s);
+}
+
+int lovr_c_score_keypoints(const void* desc1, const void* desc2, int32_t dtype, int64_t n_pairs, int32_t P, int32_t D,
+                           const int32_t* patch_idx, int32_t K, int32_t window, int32_t soft, float anno_size,
+                           float* kps_out, void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace lovr;
+  if (int rc = require_device()) return rc;
+  if (int rc = check_c_args(desc1, desc2, dtype, n_pairs, P, D)) return rc;
+  if (!patch_idx || !kps_out || !workspace) return fail(LOVR_E_ARG, "c_score_keypoints: null pointer");
+  if (K <= 0 || K > kMaxKps) return fail(LOVR_E_UNSUPPORTED, "c_score_keypoints: K=%d outside [1,%d]", K, kMaxKps);
+  if (D % 32) return fail(LOVR_E_ARG, "c_score_keypoints: D=%d must be a multiple of 32", D);
+  const int PP = P * P;
+  const size_t need = static_cast<size_t>(n_pairs) * K * PP * 4;
+  if (workspace_bytes < need) return fail(LOVR_E_NOMEM, "c_score_keypoints workspace %zu < %zu", workspace_bytes, need);
+  if (n_pairs > 65535) return fail(LOVR_E_ARG, "c_score_keypoints: at most 65535 pairs per call");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  float* rows = static_cast<float*>(workspace);
+  const size_t smem = static_cast<size_t>(K) * D * 4;
+  const int rpb = 64;
+  dim3 grid((PP + rpb - 1) / rpb, static_cast<unsigned>(n_pairs));
+  if (dtype == LOVR_DT_F32) {
+    static size_t set_for = 0;
+    if (smem > set_for) {
+      CUDA_TRY(cudaFuncSetAttribute(kp_sim_rows_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      set_for = smem;
+    }
+    kp_sim_rows_kernel<float><<<grid, 256, smem, s>>>(static_cast<const float*>(desc1), static_cast<const float*>(desc2),
+                                                      patch_idx, K, PP, D, rpb, rows);
+  } else {
+    static size_t set_for = 0;
+    if (smem > set_for) {
+      CUDA_TRY(cudaFuncSetAttribute(kp_sim_rows_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      set_for = smem;
+    }
+    kp_sim_rows_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>(static_cast<const __nv_bfloat16*>(desc1),
+                                                              static_cast<const __nv_bfloat16*>(desc2), patch_idx, K, PP, D,
+                                                              rpb, rows);
+  }
+  LAUNCH_CHECK("kp_sim_rows_kernel");
+  return launch_flow_rows(rows, PP, static_cast<size_t>(n_pairs) * K, P, window, soft, anno_size / P, kps_out, nullptr, s);
+}
+
+int lovr_pck(const float* pred, const float* gt, const uint8_t* visible, const float* thresholds, int64_t n_pairs,
+             int32_t K, float* out, void* stream) {
+  if (int rc = require_device()) return rc;
+  if (!pred || !gt || !visible || !thresholds || !out) return fail(LOVR_E_ARG, "pck: null pointer");
+  if (n_pairs <= 0) return 0;
+  lovr::pck_kernel<<<static_cast<unsigned>((n_pairs + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      pred, gt, visible, thresholds, static_cast<int>(n_pairs), K, out);
+  LAUNCH_CHECK("pck_kernel");
   return 0;
 }
 

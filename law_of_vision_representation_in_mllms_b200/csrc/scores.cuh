@@ -7,16 +7,19 @@ namespace lovr {
 
 // Scale that turns a raw dot product into the reference's cosine (A_score/compute.py:12-15,64-65):
 //   n(x) = x / (||x|| + 1e-10);  F.cosine_similarity divides by max(||n(x)||, 1e-8).
-__device__ __forceinline__ float inv_norm_scale(float sumsq) {
+//   mode 1 (C score, C_score/pck_train.py:24-29): only n(x) = x / (||x|| + 1e-10).
+__device__ __forceinline__ float inv_norm_scale(float sumsq, int mode = 0) {
   const float nrm = sqrtf(sumsq);
   const float denom1 = nrm + 1e-10f;
+  if (mode == 1) return 1.0f / denom1;
   const float nn = nrm / denom1;  // norm of the normalised vector
   return 1.0f / (denom1 * fmaxf(nn, 1e-8f));
 }
 
 // bf16 rows [rows, D] -> inv[rows]; one warp per row, 16-byte loads.
+// inv index = (row / rows_per_batch) * inv_ld + row % rows_per_batch (padded per-batch vectors for the GEMM epilogue).
 __global__ void rownorm_inv_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ inv, size_t rows,
-                                        int D) {
+                                        int D, int mode = 0, int rows_per_batch = 0x7fffffff, int inv_ld = 0) {
   const int lane = threadIdx.x & 31;
   const size_t row = blockIdx.x * static_cast<size_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -32,7 +35,7 @@ __global__ void rownorm_inv_bf16_kernel(const __nv_bfloat16* __restrict__ x, flo
     }
   }
   s = warp_sum(s);
-  if (lane == 0) inv[row] = inv_norm_scale(s);
+  if (lane == 0) inv[(row / rows_per_batch) * inv_ld + row % rows_per_batch] = inv_norm_scale(s, mode);
 }
 
 // fp32 rows [rows, D] -> bf16 [rows, 3D] and inv[rows].
@@ -40,7 +43,8 @@ __global__ void rownorm_inv_bf16_kernel(const __nv_bfloat16* __restrict__ x, flo
 //   side 0 ("other"): [hi | lo | hi]      side 1 ("ref"): [hi | hi | lo]
 // so one K=3D GEMM yields  hi·hi + lo·hi + hi·lo  (the dropped lo·lo term is ~2^-18 relative).
 __global__ void split3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, float* __restrict__ inv,
-                              size_t rows, int D, int side) {
+                              size_t rows, int D, int side, int mode = 0, int rows_per_batch = 0x7fffffff,
+                              int inv_ld = 0) {
   const int lane = threadIdx.x & 31;
   const size_t row = blockIdx.x * static_cast<size_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -69,7 +73,7 @@ __global__ void split3_kernel(const float* __restrict__ x, __nv_bfloat16* __rest
     o2[2 * seg + i] = (side == 0) ? whi : wlo;
   }
   s = warp_sum(s);
-  if (lane == 0) inv[row] = inv_norm_scale(s);
+  if (lane == 0) inv[(row / rows_per_batch) * inv_ld + row % rows_per_batch] = inv_norm_scale(s, mode);
 }
 
 // pair_score[b] = mean_i rowmax[b, i]; one block per pair, fixed-order tree (deterministic).

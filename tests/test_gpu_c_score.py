@@ -1,0 +1,98 @@
+"""C score on the device against fixtures produced by the reference's own utils_correspondence.py
+(tests/golden/c_score.pt) and the CPU oracle.  Tolerance: 1e-5 relative on predicted coordinates (north_star;
+SURVEY.md App. D: apply it relative — fp32 ulp at ~800 px is 6e-5), i.e. |dx| <= 1e-5 * 840 px, and exact PCK."""
+import os
+
+import pytest
+import torch
+
+from law_of_vision_representation_in_mllms_b200 import c_score as CS
+from oracle import c_score_oracle as co
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+PIX_TOL = 1e-5 * 840 + 2e-4     # 1e-5 relative of the annotation frame + fp32 ulp at 800 px
+
+
+@pytest.fixture(scope="module")
+def c_gold(golden_dir):
+    return torch.load(os.path.join(golden_dir, "c_score.pt"))
+
+
+@pytest.mark.parametrize("cname", list(synth.C_SCORE_CASES))
+def test_keypoint_transformation_matches_reference(cname, c_gold):
+    cfg = synth.C_SCORE_CASES[cname]
+    d1, d2, kps = synth.c_score_pair(cfg)
+    rec = c_gold[cname]
+    idx = CS.kpts_to_patch_idx(kps, cfg["P"])
+    assert torch.equal(torch.as_tensor(idx), rec["patch_idx"])
+    soft = CS.keypoint_transformation(d1.cuda(), d2.cuda(), idx[None], soft=True, window=cfg["window"])[0].cpu()
+    hard = CS.keypoint_transformation(d1.cuda(), d2.cuda(), idx[None], soft=False)[0].cpu()
+    assert (soft - rec["soft"]).abs().max() < PIX_TOL, (soft - rec["soft"]).abs().max()
+    assert torch.equal(hard, rec["hard"])
+
+
+@pytest.mark.parametrize("cname", list(synth.C_SCORE_CASES))
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_dense_flow_matches_reference(cname, dtype, c_gold):
+    cfg = synth.C_SCORE_CASES[cname]
+    d1, d2, _ = synth.c_score_pair(cfg)
+    P = cfg["P"]
+    if dtype == torch.float32:
+        want_flow, want_arg = c_gold[cname]["flow"], c_gold[cname]["argmax"]
+    else:      # bf16 descriptors: the oracle sees the same rounded values
+        d1, d2 = d1.bfloat16(), d2.bfloat16()
+        sim = torch.matmul(co.normalize_feats(d1.float()), co.normalize_feats(d2.float()).permute(0, 2, 1))[0]
+        want_flow, want_arg = co.get_flow(sim, cfg["window"], P), sim.argmax(-1)
+    flow, amax = CS.get_flow(d1.cuda(), d2.cuda(), window=cfg["window"], return_argmax=True)
+    flow, amax = flow[0].cpu(), amax[0].cpu().long()
+    same = amax == want_arg
+    # a near-tie (gap below the 1e-6 GEMM error) may legitimately pick the other maximum: allow a few rows
+    assert same.float().mean() > 0.999, same.float().mean()
+    err = (flow - want_flow)[same].abs().max()
+    assert err < 1e-5 * P + 2e-5, err
+
+
+def test_dense_flow_and_keypoint_rows_agree():
+    cfg = synth.C_SCORE_CASES["p24_corr"]
+    d1, d2, kps = synth.c_score_pair(cfg)
+    P = cfg["P"]
+    idx = CS.kpts_to_patch_idx(kps, P)
+    flow = CS.get_flow(d1.cuda(), d2.cuda(), window=5)[0].cpu()
+    kp = CS.keypoint_transformation(d1.cuda(), d2.cuda(), idx[None])[0].cpu()
+    stride = 840 / P
+    want = flow[torch.as_tensor(idx, dtype=torch.long)].clamp(0, P - 1) * stride + stride // 2
+    assert (kp - want).abs().max() < PIX_TOL
+
+
+def test_batched_pairs_pck_and_category_weighting():
+    cfgs = [synth.C_SCORE_CASES[n] for n in ("p16_rand", "p16_corr")]
+    pairs = [synth.c_score_pair(c) for c in cfgs]
+    d1 = torch.cat([p[0] for p in pairs]).cuda()
+    d2 = torch.cat([p[1] for p in pairs]).cuda()
+    kps1 = torch.stack([p[2] for p in pairs])
+    g = torch.Generator().manual_seed(5)
+    kps2 = torch.rand(2, 12, 3, generator=g) * 839
+    kps2[..., 2] = (torch.rand(2, 12, generator=g) > 0.3).float()
+    thr = torch.tensor([400.0, 650.0])
+    sums, pred = CS.c_score(d1, d2, kps1, kps2, thr, categories=[0, 2], n_categories=3)
+    for b in range(2):
+        d1n, d2n = co.normalize_feats(pairs[b][0]), co.normalize_feats(pairs[b][1])
+        idx = co.kpts_to_patch_idx(kps1[b], 16)
+        want = co.keypoint_transformation(d1n, d2n, idx, 16)
+        assert (pred[b].cpu() - want).abs().max() < PIX_TOL
+        vis = (kps1[b, :, 2] * kps2[b, :, 2]) > 0
+        pck = co.pck_per_image(want, kps2[b, :, :2], vis, thr[b])
+        cat = [0, 2][b]
+        assert torch.allclose(sums[cat, :3].cpu().float(), torch.tensor(pck), atol=1e-6)
+        assert sums[cat, 3].item() == 1
+    c10, c05, c01 = CS.weighted_c_score(sums)
+    assert abs(c10 - co.weighted_pck([sums[0, 0].item(), sums[2, 0].item()], [1, 1])) < 1e-9
+
+
+def test_feature_map_layout_roundtrip():
+    from law_of_vision_representation_in_mllms_b200.extract import to_c_score_layout
+    f = torch.arange(2 * 3 * 4, dtype=torch.float32).reshape(1, 6, 4)     # [1,P=6 (h=2,w=3),C=4]
+    fmap = to_c_score_layout(f, 2, 3)                                      # extract_feature.py:82
+    assert tuple(fmap.shape) == (1, 4, 2, 3)
+    assert torch.equal(CS.desc_from_feature_map(fmap), f)                  # pck_train.py:38-39 undoes it
