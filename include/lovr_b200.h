@@ -61,25 +61,27 @@ typedef struct {
   int32_t layerscale;        /* DINOv2 LayerScale */
   float ln_eps;
   int32_t patch_k_padded;    /* 3*patch*patch rounded up to a multiple of 64 (im2col K) */
+  int32_t operand_dtype;     /* LOVR_DT_BF16 or LOVR_DT_F16: 16-bit format of the tensor-core operands (activations AND
+                                the weight matrices below); accumulation, residual stream, LayerNorm, softmax are fp32 */
 } lovr_tower_config;
 
 typedef struct {
   const float* ln1_w; const float* ln1_b;
-  const void* qkv_w;  /* bf16 [3D, D] rows = q,k,v output features */
+  const void* qkv_w;  /* 16-bit (operand_dtype) [3D, D] rows = q,k,v output features */
   const float* qkv_b; /* [3D] */
-  const void* o_w;    /* bf16 [D, D] */
+  const void* o_w;    /* 16-bit [D, D] */
   const float* o_b;
   const float* ls1;   /* [D] or NULL */
   const float* ln2_w; const float* ln2_b;
-  const void* fc1_w;  /* bf16 [I, D] */
+  const void* fc1_w;  /* 16-bit [I, D] */
   const float* fc1_b;
-  const void* fc2_w;  /* bf16 [D, I] */
+  const void* fc2_w;  /* 16-bit [D, I] */
   const float* fc2_b;
   const float* ls2;   /* [D] or NULL */
 } lovr_layer_weights;
 
 typedef struct {
-  const void* patch_w;   /* bf16 [D, patch_k_padded], k = c*P*P + py*P + px, zero padded */
+  const void* patch_w;   /* 16-bit [D, patch_k_padded], k = c*P*P + py*P + px, zero padded */
   const float* patch_b;  /* [D] or NULL (CLIP has no conv bias) */
   const float* cls;      /* [D] or NULL */
   const float* pos;      /* [T, D] (already interpolated for image_size: DINOv2) */
@@ -105,18 +107,20 @@ int lovr_tower_forward(lovr_tower_t* t, const void* pixels, int32_t pixel_dtype,
 /* ---------------------------------------------------------------------------------------------------
  * Building blocks (exported so each kernel is parity-tested in isolation through the same ABI).
  * ------------------------------------------------------------------------------------------------- */
-/* C[M,N] = epilogue(A[M,K] bf16 · W[N,K]^T bf16): nn.Linear semantics. lda/ldw/ldc in elements.
- * LOVR_EPI_BF16: C bf16 = act(acc+bias). LOVR_EPI_F32: C fp32 = acc+bias.
+/* operand_dtype (LOVR_DT_BF16 | LOVR_DT_F16) = the 16-bit format of A, W and of 16-bit outputs; fp32 accumulate.
+ * C[M,N] = epilogue(A[M,K] · W[N,K]^T): nn.Linear semantics. lda/ldw/ldc in elements.
+ * LOVR_EPI_BF16: C 16-bit = act(acc+bias). LOVR_EPI_F32: C fp32 = acc+bias.
  * LOVR_EPI_RESID_F32: C fp32 += colscale*(acc+bias) in place. */
 int lovr_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int32_t M,
-                   int32_t N, int32_t K, int32_t epi, int32_t act, const float* bias, const float* colscale,
-                   void* stream);
-int lovr_layernorm_bf16(const float* x, const float* gamma, const float* beta, float eps, void* y_bf16,
-                        int64_t rows, int32_t D, void* stream);
-/* qkv bf16 [n_img*T, 3*H*64] -> out bf16 [n_img*T, H*64]; softmax(q k^T / 8) v per (image, head) */
-int lovr_attention(const void* qkv, void* out, int32_t n_img, int32_t T, int32_t H, int32_t impl, void* stream);
-int lovr_im2col(const void* pixels, int32_t pixel_dtype, void* cols_bf16, int32_t n_img, int32_t image_size,
-                int32_t patch, int32_t k_padded, void* stream);
+                   int32_t N, int32_t K, int32_t epi, int32_t act, int32_t operand_dtype, const float* bias,
+                   const float* colscale, void* stream);
+int lovr_layernorm_bf16(const float* x, const float* gamma, const float* beta, float eps, void* y_16bit,
+                        int64_t rows, int32_t D, int32_t operand_dtype, void* stream);
+/* qkv 16-bit [n_img*T, 3*H*64] -> out 16-bit [n_img*T, H*64]; softmax(q k^T / 8) v per (image, head) */
+int lovr_attention(const void* qkv, void* out, int32_t n_img, int32_t T, int32_t H, int32_t impl,
+                   int32_t operand_dtype, void* stream);
+int lovr_im2col(const void* pixels, int32_t pixel_dtype, void* cols_16bit, int32_t n_img, int32_t image_size,
+                int32_t patch, int32_t k_padded, int32_t operand_dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * A score (replaces the per-pair arithmetic of A_score/compute.py:54-72):

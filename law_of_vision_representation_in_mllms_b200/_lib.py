@@ -27,7 +27,7 @@ EXPORTS = [
 class TowerConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("hidden_size", "intermediate_size", "num_layers", "num_heads", "image_size",
                                          "patch_size", "act", "has_cls", "pre_ln", "layerscale")] + \
-               [("ln_eps", C.c_float), ("patch_k_padded", C.c_int32)]
+               [("ln_eps", C.c_float), ("patch_k_padded", C.c_int32), ("operand_dtype", C.c_int32)]
 
 
 class LayerWeights(C.Structure):
@@ -74,13 +74,13 @@ def lib():
     L.lovr_tower_forward.restype = C.c_int
     L.lovr_tower_forward.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32, i64, i64, i32, vp]
     L.lovr_gemm_bf16.restype = C.c_int
-    L.lovr_gemm_bf16.argtypes = [vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, i32, vp, vp, vp]
+    L.lovr_gemm_bf16.argtypes = [vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, i32, i32, vp, vp, vp]
     L.lovr_layernorm_bf16.restype = C.c_int
-    L.lovr_layernorm_bf16.argtypes = [vp, vp, vp, f32, vp, i64, i32, vp]
+    L.lovr_layernorm_bf16.argtypes = [vp, vp, vp, f32, vp, i64, i32, i32, vp]
     L.lovr_attention.restype = C.c_int
-    L.lovr_attention.argtypes = [vp, vp, i32, i32, i32, i32, vp]
+    L.lovr_attention.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
     L.lovr_im2col.restype = C.c_int
-    L.lovr_im2col.argtypes = [vp, i32, vp, i32, i32, i32, i32, vp]
+    L.lovr_im2col.argtypes = [vp, i32, vp, i32, i32, i32, i32, i32, vp]
     L.lovr_a_score_workspace_bytes.restype = sz
     L.lovr_a_score_workspace_bytes.argtypes = [i32, i64, i32, i32, i32]
     L.lovr_a_score_maxcos.restype = C.c_int

@@ -24,7 +24,7 @@ struct AttnArgs {
   int nb;       // ceil(T / 128)
   int last_w;   // width of the last KV block, multiple of 32
   float scale;  // head_dim^-0.5
-  __nv_bfloat16* out;  // [N*T, H*64]
+  uint16_t* out;  // [N*T, H*64], 16-bit operand format
 };
 
 inline size_t attn_smem_bytes(int nb) {
@@ -37,6 +37,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+template <bool F16>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs p) {
   extern __shared__ uint8_t smem_raw[];
@@ -109,9 +110,9 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnAr
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc_s_full = make_idesc_bf16(128, 128, 0, 0);
-      const uint32_t idesc_s_last = make_idesc_bf16(128, p.last_w, 0, 0);
-      const uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);  // B (=V) is MN-major
+      const uint32_t idesc_s_full = make_idesc_16(128, 128, 0, 0, F16);
+      const uint32_t idesc_s_last = make_idesc_16(128, p.last_w, 0, 0, F16);
+      const uint32_t idesc_o = make_idesc_16(128, 64, 0, 1, F16);  // B (=V) is MN-major
       uint32_t sc = 0, pc = 0;
       mbar_wait(k_full, 0);
       auto issue_qk = [&](int qb, int j) {
@@ -214,7 +215,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnAr
               e0 = (c * 32 + i < valid) ? e0 : 0.f;
               e1 = (c * 32 + i + 1 < valid) ? e1 : 0.f;
               l += e0 + e1;
-              pk[(c * 32 + i) >> 1] = pack_bf16x2(e0, e1);
+              pk[(c * 32 + i) >> 1] = pack16x2<F16>(e0, e1);
             }
           }
         }
@@ -252,10 +253,10 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnAr
         for (int q = 0; q < 8; ++q) {
           uint4 w;
           const uint32_t* src = (q < 4) ? &o0[q * 8] : &o1[(q - 4) * 8];
-          w.x = pack_bf16x2(__uint_as_float(src[0]) * inv, __uint_as_float(src[1]) * inv);
-          w.y = pack_bf16x2(__uint_as_float(src[2]) * inv, __uint_as_float(src[3]) * inv);
-          w.z = pack_bf16x2(__uint_as_float(src[4]) * inv, __uint_as_float(src[5]) * inv);
-          w.w = pack_bf16x2(__uint_as_float(src[6]) * inv, __uint_as_float(src[7]) * inv);
+          w.x = pack16x2<F16>(__uint_as_float(src[0]) * inv, __uint_as_float(src[1]) * inv);
+          w.y = pack16x2<F16>(__uint_as_float(src[2]) * inv, __uint_as_float(src[3]) * inv);
+          w.z = pack16x2<F16>(__uint_as_float(src[4]) * inv, __uint_as_float(src[5]) * inv);
+          w.w = pack16x2<F16>(__uint_as_float(src[6]) * inv, __uint_as_float(src[7]) * inv);
           dst[q] = w;
         }
       }

@@ -18,7 +18,7 @@ namespace lovr {
 
 enum : int { ACT_NONE = 0, ACT_QUICK_GELU = 1, ACT_GELU_ERF = 2, ACT_GELU_TANH = 3 };
 enum : int {
-  EPI_BF16 = 0,      // C bf16  = act(acc + bias)
+  EPI_BF16 = 0,      // C 16-bit (operand format) = act(acc + bias)
   EPI_RESID_F32 = 1, // C fp32 += colscale * (acc + bias)          (in place residual stream)
   EPI_F32 = 2,       // C fp32  = acc + bias
   EPI_ROWMAX = 3     // rowmax[b,row] = rowscale[b,row] * max_col(acc * colscale[b,col]), cols < n_valid
@@ -71,14 +71,14 @@ __device__ __forceinline__ float apply_act(float x) {
   return x;
 }
 
-template <int BN, int EPI, int ACT>
+template <int BN, int EPI, int ACT, bool F16>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const GemmArgs p) {
   using L = GemmSmem<BN>;
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N constraint for M=128");
   constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  constexpr uint32_t kIdesc = make_idesc_bf16(kBM, BN, 0, 0);
+  constexpr uint32_t kIdesc = make_idesc_16(kBM, BN, 0, 0, F16);  // operands fp16 or bf16, fp32 accumulate
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -231,8 +231,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const float x = __uint_as_float(cc < 32 ? r0[cc] : r1[cc - 32]) + bb[e];
                 v[e] = apply_act<ACT>(x);
               }
-              st_shared_v4(buf_row + ((j ^ row_sw) << 4), pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
-                           pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+              st_shared_v4(buf_row + ((j ^ row_sw) << 4), pack16x2<F16>(v[0], v[1]), pack16x2<F16>(v[2], v[3]),
+                           pack16x2<F16>(v[4], v[5]), pack16x2<F16>(v[6], v[7]));
             }
             fence_proxy_async_smem();
             __syncwarp();

@@ -166,10 +166,10 @@ void prof_end(cudaStream_t s, size_t idx) {
 }
 
 // ------------------------------------------------------------------------------------ GEMM launch
-template <int BN, int EPI, int ACT>
+template <int BN, int EPI, int ACT, bool F16>
 int launch_gemm_inst(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const lovr::GemmArgs& args,
                      cudaStream_t s) {
-  auto kern = lovr::gemm_tcgen05_kernel<BN, EPI, ACT>;
+  auto kern = lovr::gemm_tcgen05_kernel<BN, EPI, ACT, F16>;
   static bool attr_set = false;
   const int smem = lovr::GemmSmem<BN>::kTotal;
   if (!attr_set) {
@@ -189,31 +189,32 @@ int launch_gemm_inst(const CUtensorMap& a, const CUtensorMap& b, const CUtensorM
   return 0;
 }
 
-int launch_gemm(int bn, int epi, int act, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c,
+int launch_gemm(int bn, int epi, int act, bool f16, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c,
                 const lovr::GemmArgs& args, cudaStream_t s) {
   using namespace lovr;
   if (args.K % kBK) return fail(LOVR_E_ARG, "gemm: K=%d must be a multiple of 64", args.K);
-  if (epi == EPI_BF16 && bn == 256) {
-    switch (act) {
-      case ACT_NONE: return launch_gemm_inst<256, EPI_BF16, ACT_NONE>(a, b, c, args, s);
-      case ACT_QUICK_GELU: return launch_gemm_inst<256, EPI_BF16, ACT_QUICK_GELU>(a, b, c, args, s);
-      case ACT_GELU_ERF: return launch_gemm_inst<256, EPI_BF16, ACT_GELU_ERF>(a, b, c, args, s);
-      case ACT_GELU_TANH: return launch_gemm_inst<256, EPI_BF16, ACT_GELU_TANH>(a, b, c, args, s);
-    }
-  }
-  if (epi == EPI_RESID_F32 && bn == 256) return launch_gemm_inst<256, EPI_RESID_F32, ACT_NONE>(a, b, c, args, s);
-  if (epi == EPI_F32 && bn == 256) return launch_gemm_inst<256, EPI_F32, ACT_NONE>(a, b, c, args, s);
-  if (epi == EPI_ROWMAX && bn == 128) return launch_gemm_inst<128, EPI_ROWMAX, ACT_NONE>(a, b, c, args, s);
-  if (epi == EPI_ROWMAX && bn == 192) return launch_gemm_inst<192, EPI_ROWMAX, ACT_NONE>(a, b, c, args, s);
-  if (epi == EPI_ROWMAX && bn == 256) return launch_gemm_inst<256, EPI_ROWMAX, ACT_NONE>(a, b, c, args, s);
-  return fail(LOVR_E_UNSUPPORTED, "gemm: no instance for BN=%d epi=%d act=%d", bn, epi, act);
+#define LOVR_GEMM_CASE(BN_, EPI_, ACT_)                                                   \
+  if (bn == BN_ && epi == EPI_ && act == ACT_)                                            \
+    return f16 ? launch_gemm_inst<BN_, EPI_, ACT_, true>(a, b, c, args, s)                \
+               : launch_gemm_inst<BN_, EPI_, ACT_, false>(a, b, c, args, s);
+  LOVR_GEMM_CASE(256, EPI_BF16, ACT_NONE)
+  LOVR_GEMM_CASE(256, EPI_BF16, ACT_QUICK_GELU)
+  LOVR_GEMM_CASE(256, EPI_BF16, ACT_GELU_ERF)
+  LOVR_GEMM_CASE(256, EPI_BF16, ACT_GELU_TANH)
+  LOVR_GEMM_CASE(256, EPI_RESID_F32, ACT_NONE)
+  LOVR_GEMM_CASE(256, EPI_F32, ACT_NONE)
+#undef LOVR_GEMM_CASE
+  if (!f16 && epi == EPI_ROWMAX && bn == 128) return launch_gemm_inst<128, EPI_ROWMAX, ACT_NONE, false>(a, b, c, args, s);
+  if (!f16 && epi == EPI_ROWMAX && bn == 192) return launch_gemm_inst<192, EPI_ROWMAX, ACT_NONE, false>(a, b, c, args, s);
+  if (!f16 && epi == EPI_ROWMAX && bn == 256) return launch_gemm_inst<256, EPI_ROWMAX, ACT_NONE, false>(a, b, c, args, s);
+  return fail(LOVR_E_UNSUPPORTED, "gemm: no instance for BN=%d epi=%d act=%d f16=%d", bn, epi, act, int(f16));
 }
 
 constexpr int kDenseBN = 256;
 
 // Dense layer: A [M,K] bf16 (lda), W [N,K] bf16 (ldw), C [M,N] (ldc; bf16 or fp32 by epilogue).
 int dense_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int M, int N, int K,
-               int epi, int act, const float* bias, const float* colscale, cudaStream_t s) {
+               int epi, int act, bool f16, const float* bias, const float* colscale, cudaStream_t s) {
   if (N % kDenseBN) return fail(LOVR_E_ARG, "gemm: N=%d must be a multiple of %d", N, kDenseBN);
   if (M <= 0) return 0;
   CUtensorMap ta, tb, tc;
@@ -229,7 +230,7 @@ int dense_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, 
   g.M = M; g.N = N; g.K = K; g.batch = 1; g.n_inner = 1;
   g.bias = bias; g.colscale = colscale; g.rowscale = nullptr; g.rowmax = nullptr; g.n_valid = N; g.scale_ld = 0;
   if (epi == lovr::EPI_F32) g.colscale = nullptr;  // (similarity scaling is only used by the C-score path)
-  return launch_gemm(kDenseBN, epi, act, ta, tb, tc, g, s);
+  return launch_gemm(kDenseBN, epi, act, f16, ta, tb, tc, g, s);
 }
 
 // ------------------------------------------------------------------------------------ row-wise launches
@@ -240,34 +241,48 @@ int dispatch_width(int D, F4 f1024, F3 f768) {
   return fail(LOVR_E_UNSUPPORTED, "hidden size %d not instantiated (1024, 768)", D);
 }
 
-int launch_layernorm(const float* x, const float* g, const float* b, float eps, void* y, int64_t rows, int D,
+int launch_layernorm(const float* x, const float* g, const float* b, float eps, void* y, int64_t rows, int D, bool f16,
                      cudaStream_t s) {
   if (rows <= 0) return 0;
   const int wpb = 8;
   const unsigned grid = static_cast<unsigned>((rows + wpb - 1) / wpb);
-  auto y16 = static_cast<__nv_bfloat16*>(y);
+  auto y16 = static_cast<uint16_t*>(y);
   int rc = dispatch_width(
       D,
-      [&] { lovr::layernorm_bf16_kernel<8><<<grid, wpb * 32, 0, s>>>(x, g, b, eps, y16, rows); return 0; },
-      [&] { lovr::layernorm_bf16_kernel<6><<<grid, wpb * 32, 0, s>>>(x, g, b, eps, y16, rows); return 0; });
+      [&] {
+        if (f16) lovr::layernorm_bf16_kernel<8, true><<<grid, wpb * 32, 0, s>>>(x, g, b, eps, y16, rows);
+        else lovr::layernorm_bf16_kernel<8, false><<<grid, wpb * 32, 0, s>>>(x, g, b, eps, y16, rows);
+        return 0;
+      },
+      [&] {
+        if (f16) lovr::layernorm_bf16_kernel<6, true><<<grid, wpb * 32, 0, s>>>(x, g, b, eps, y16, rows);
+        else lovr::layernorm_bf16_kernel<6, false><<<grid, wpb * 32, 0, s>>>(x, g, b, eps, y16, rows);
+        return 0;
+      });
   if (rc) return rc;
   LAUNCH_CHECK("layernorm_bf16_kernel");
   return 0;
 }
 
-int launch_attention(const void* qkv, void* out, int n_img, int T, int H, int impl, cudaStream_t s) {
+int launch_attention(const void* qkv, void* out, int n_img, int T, int H, int impl, bool f16, cudaStream_t s) {
   if (n_img <= 0) return 0;
   const int D = H * 64;
   if (impl == LOVR_ATTN_SIMT_CHECK) {
     const size_t smem = lovr::attn_simt_smem_bytes(T);
     static size_t set_for = 0;
     if (smem > set_for) {
-      CUDA_TRY(cudaFuncSetAttribute(lovr::attention_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      CUDA_TRY(cudaFuncSetAttribute(lovr::attention_simt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(smem)));
+      CUDA_TRY(cudaFuncSetAttribute(lovr::attention_simt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     static_cast<int>(smem)));
       set_for = smem;
     }
-    lovr::attention_simt_kernel<<<n_img * H, lovr::kSimtAttnWarps * 32, smem, s>>>(
-        static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), T, H, 0.125f);
+    if (f16)
+      lovr::attention_simt_kernel<true><<<n_img * H, lovr::kSimtAttnWarps * 32, smem, s>>>(
+          static_cast<const uint16_t*>(qkv), static_cast<uint16_t*>(out), T, H, 0.125f);
+    else
+      lovr::attention_simt_kernel<false><<<n_img * H, lovr::kSimtAttnWarps * 32, smem, s>>>(
+          static_cast<const uint16_t*>(qkv), static_cast<uint16_t*>(out), T, H, 0.125f);
     LAUNCH_CHECK("attention_simt_kernel");
     return 0;
   }
@@ -276,28 +291,31 @@ int launch_attention(const void* qkv, void* out, int n_img, int T, int H, int im
   const int rem = T - 128 * (nb - 1);
   lovr::AttnArgs a{};
   a.T = T; a.H = H; a.nb = nb; a.last_w = (rem + 31) / 32 * 32; a.scale = 0.125f;
-  a.out = static_cast<__nv_bfloat16*>(out);
+  a.out = static_cast<uint16_t*>(out);
   CUtensorMap tq;
   int rc;
   if ((rc = make_tmap(&tq, qkv, 2, 3 * D, T, n_img, 3 * D, static_cast<uint64_t>(3) * D * T, 64, 128))) return rc;
   const size_t smem = lovr::attn_smem_bytes(nb);
   static size_t set_for = 0;
   if (smem > set_for) {
-    CUDA_TRY(cudaFuncSetAttribute(lovr::attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CUDA_TRY(cudaFuncSetAttribute(lovr::attention_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem)));
+    CUDA_TRY(cudaFuncSetAttribute(lovr::attention_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem)));
     set_for = smem;
   }
-  lovr::attention_tcgen05_kernel<<<n_img * H, lovr::kAttnThreads, smem, s>>>(tq, a);
+  if (f16) lovr::attention_tcgen05_kernel<true><<<n_img * H, lovr::kAttnThreads, smem, s>>>(tq, a);
+  else lovr::attention_tcgen05_kernel<false><<<n_img * H, lovr::kAttnThreads, smem, s>>>(tq, a);
   LAUNCH_CHECK("attention_tcgen05_kernel");
   return 0;
 }
 
-int launch_im2col(const void* pixels, int dt, void* cols, int n_img, int R, int P, int Kpad, cudaStream_t s) {
+int launch_im2col(const void* pixels, int dt, void* cols, int n_img, int R, int P, int Kpad, bool f16, cudaStream_t s) {
   if (n_img <= 0) return 0;
   const int G = R / P;
   const size_t total = static_cast<size_t>(n_img) * G * G * Kpad;
   const unsigned grid = static_cast<unsigned>(std::min<size_t>((total + 255) / 256, 148 * 32));
-  lovr::im2col_kernel<<<grid, 256, 0, s>>>(pixels, dt, static_cast<__nv_bfloat16*>(cols), n_img, R, P, G, Kpad);
+  lovr::im2col_kernel<<<grid, 256, 0, s>>>(pixels, dt, static_cast<uint16_t*>(cols), n_img, R, P, G, Kpad, f16 ? 1 : 0);
   LAUNCH_CHECK("im2col_kernel");
   return 0;
 }
@@ -393,6 +411,8 @@ int lovr_tower_create(lovr_tower_t** out, const lovr_tower_config* cfg, const lo
   if (cfg->patch_k_padded % 64 || cfg->patch_k_padded < 3 * cfg->patch_size * cfg->patch_size)
     return fail(LOVR_E_ARG, "patch_k_padded must be a multiple of 64 covering 3*P*P");
   if (cfg->intermediate_size % 256 || cfg->hidden_size % 256) return fail(LOVR_E_UNSUPPORTED, "widths must be multiples of 256");
+  if (cfg->operand_dtype != LOVR_DT_BF16 && cfg->operand_dtype != LOVR_DT_F16)
+    return fail(LOVR_E_ARG, "operand_dtype must be LOVR_DT_BF16 or LOVR_DT_F16");
   const WsLayout l = ws_layout(*cfg, max_batch);
   if (workspace_bytes < l.total) return fail(LOVR_E_NOMEM, "workspace %zu < required %zu", workspace_bytes, l.total);
   if (reinterpret_cast<uintptr_t>(workspace) & 1023) return fail(LOVR_E_ARG, "workspace must be 1024-byte aligned");
@@ -428,6 +448,7 @@ int lovr_tower_forward(lovr_tower_t* t, const void* pixels, int32_t pixel_dtype,
   const lovr_tower_config& c = t->cfg;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int D = c.hidden_size, I = c.intermediate_size, T = t->T, G = t->G;
+  const bool f16 = c.operand_dtype == LOVR_DT_F16;
   const int M = n_img * T;
   const int Mp = n_img * G * G;
   int rc;
@@ -435,9 +456,9 @@ int lovr_tower_forward(lovr_tower_t* t, const void* pixels, int32_t pixel_dtype,
   void* cols = t->big;
   float* patch_out = reinterpret_cast<float*>(static_cast<uint8_t*>(t->big) +
                                               align_up(static_cast<size_t>(Mp) * c.patch_k_padded * 2, 1024));
-  if ((rc = launch_im2col(pixels, pixel_dtype, cols, n_img, c.image_size, c.patch_size, c.patch_k_padded, s))) return rc;
+  if ((rc = launch_im2col(pixels, pixel_dtype, cols, n_img, c.image_size, c.patch_size, c.patch_k_padded, f16, s))) return rc;
   if ((rc = dense_gemm(cols, c.patch_k_padded, t->w.patch_w, c.patch_k_padded, patch_out, D, Mp, D, c.patch_k_padded,
-                       EPI_F32, ACT_NONE, t->w.patch_b, nullptr, s)))
+                       EPI_F32, ACT_NONE, f16, t->w.patch_b, nullptr, s)))
     return rc;
   {
     const int wpb = 8;
@@ -460,14 +481,14 @@ int lovr_tower_forward(lovr_tower_t* t, const void* pixels, int32_t pixel_dtype,
   // ---- encoder layers
   for (int li = 0; li < layers_to_run; ++li) {
     const lovr_layer_weights& lw = t->layers[li];
-    if ((rc = launch_layernorm(t->x, lw.ln1_w, lw.ln1_b, c.ln_eps, t->ln, M, D, s))) return rc;
-    if ((rc = dense_gemm(t->ln, D, lw.qkv_w, D, t->big, 3 * D, M, 3 * D, D, EPI_BF16, ACT_NONE, lw.qkv_b, nullptr, s)))
+    if ((rc = launch_layernorm(t->x, lw.ln1_w, lw.ln1_b, c.ln_eps, t->ln, M, D, f16, s))) return rc;
+    if ((rc = dense_gemm(t->ln, D, lw.qkv_w, D, t->big, 3 * D, M, 3 * D, D, EPI_BF16, ACT_NONE, f16, lw.qkv_b, nullptr, s)))
       return rc;
-    if ((rc = launch_attention(t->big, t->ln, n_img, T, c.num_heads, attn_impl, s))) return rc;
-    if ((rc = dense_gemm(t->ln, D, lw.o_w, D, t->x, D, M, D, D, EPI_RESID_F32, ACT_NONE, lw.o_b, lw.ls1, s))) return rc;
-    if ((rc = launch_layernorm(t->x, lw.ln2_w, lw.ln2_b, c.ln_eps, t->ln, M, D, s))) return rc;
-    if ((rc = dense_gemm(t->ln, D, lw.fc1_w, D, t->big, I, M, I, D, EPI_BF16, c.act, lw.fc1_b, nullptr, s))) return rc;
-    if ((rc = dense_gemm(t->big, I, lw.fc2_w, I, t->x, D, M, D, I, EPI_RESID_F32, ACT_NONE, lw.fc2_b, lw.ls2, s)))
+    if ((rc = launch_attention(t->big, t->ln, n_img, T, c.num_heads, attn_impl, f16, s))) return rc;
+    if ((rc = dense_gemm(t->ln, D, lw.o_w, D, t->x, D, M, D, D, EPI_RESID_F32, ACT_NONE, f16, lw.o_b, lw.ls1, s))) return rc;
+    if ((rc = launch_layernorm(t->x, lw.ln2_w, lw.ln2_b, c.ln_eps, t->ln, M, D, f16, s))) return rc;
+    if ((rc = dense_gemm(t->ln, D, lw.fc1_w, D, t->big, I, M, I, D, EPI_BF16, c.act, f16, lw.fc1_b, nullptr, s))) return rc;
+    if ((rc = dense_gemm(t->big, I, lw.fc2_w, I, t->x, D, M, D, I, EPI_RESID_F32, ACT_NONE, f16, lw.fc2_b, lw.ls2, s)))
       return rc;
   }
   // ---- feature_select + cast into the caller's layout
@@ -496,29 +517,33 @@ int lovr_tower_forward(lovr_tower_t* t, const void* pixels, int32_t pixel_dtype,
 
 // ====================================================================================== building blocks
 int lovr_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int32_t M, int32_t N,
-                   int32_t K, int32_t epi, int32_t act, const float* bias, const float* colscale, void* stream) {
+                   int32_t K, int32_t epi, int32_t act, int32_t operand_dtype, const float* bias, const float* colscale,
+                   void* stream) {
   if (int rc = require_device()) return rc;
   if (!A || !W || !C) return fail(LOVR_E_ARG, "gemm: null pointer");
   if (epi < 0 || epi > LOVR_EPI_F32) return fail(LOVR_E_ARG, "gemm: epilogue %d", epi);
   if (epi != LOVR_EPI_BF16 && act != LOVR_ACT_NONE) return fail(LOVR_E_ARG, "gemm: activation only with the bf16 epilogue");
-  return dense_gemm(A, lda, W, ldw, C, ldc, M, N, K, epi, act, bias, colscale, static_cast<cudaStream_t>(stream));
+  return dense_gemm(A, lda, W, ldw, C, ldc, M, N, K, epi, act, operand_dtype == LOVR_DT_F16, bias, colscale,
+                    static_cast<cudaStream_t>(stream));
 }
 
 int lovr_layernorm_bf16(const float* x, const float* gamma, const float* beta, float eps, void* y, int64_t rows,
-                        int32_t D, void* stream) {
+                        int32_t D, int32_t operand_dtype, void* stream) {
   if (int rc = require_device()) return rc;
-  return launch_layernorm(x, gamma, beta, eps, y, rows, D, static_cast<cudaStream_t>(stream));
+  return launch_layernorm(x, gamma, beta, eps, y, rows, D, operand_dtype == LOVR_DT_F16, static_cast<cudaStream_t>(stream));
 }
 
-int lovr_attention(const void* qkv, void* out, int32_t n_img, int32_t T, int32_t H, int32_t impl, void* stream) {
+int lovr_attention(const void* qkv, void* out, int32_t n_img, int32_t T, int32_t H, int32_t impl, int32_t operand_dtype,
+                   void* stream) {
   if (int rc = require_device()) return rc;
-  return launch_attention(qkv, out, n_img, T, H, impl, static_cast<cudaStream_t>(stream));
+  return launch_attention(qkv, out, n_img, T, H, impl, operand_dtype == LOVR_DT_F16, static_cast<cudaStream_t>(stream));
 }
 
 int lovr_im2col(const void* pixels, int32_t pixel_dtype, void* cols, int32_t n_img, int32_t image_size, int32_t patch,
-                int32_t k_padded, void* stream) {
+                int32_t k_padded, int32_t operand_dtype, void* stream) {
   if (int rc = require_device()) return rc;
-  return launch_im2col(pixels, pixel_dtype, cols, n_img, image_size, patch, k_padded, static_cast<cudaStream_t>(stream));
+  return launch_im2col(pixels, pixel_dtype, cols, n_img, image_size, patch, k_padded, operand_dtype == LOVR_DT_F16,
+                       static_cast<cudaStream_t>(stream));
 }
 
 // ====================================================================================== A score
@@ -607,7 +632,7 @@ int lovr_a_score_maxcos(const void* other, const void* ref, int32_t dtype, int64
   g.M = x; g.N = y; g.K = K; g.batch = static_cast<int>(n_pairs);
   g.n_inner = (y + bn - 1) / bn;
   g.bias = nullptr; g.colscale = inv_r; g.rowscale = inv_o; g.rowmax = rowmax; g.n_valid = y;
-  if ((rc = launch_gemm(bn, EPI_ROWMAX, ACT_NONE, ta, tb, ta /*unused*/, g, s))) return rc;
+  if ((rc = launch_gemm(bn, EPI_ROWMAX, ACT_NONE, false, ta, tb, ta /*unused*/, g, s))) return rc;
   pair_mean_kernel<<<static_cast<unsigned>(n_pairs), 256, 0, s>>>(rowmax, pair_score, x);
   LAUNCH_CHECK("pair_mean_kernel");
   return 0;
@@ -707,7 +732,7 @@ int lovr_c_score_flow(const void* desc1, const void* desc2, int32_t dtype, int64
   GemmArgs g{};
   g.M = PP; g.N = PP; g.K = K; g.batch = static_cast<int>(n_pairs); g.n_inner = 1;
   g.bias = nullptr; g.colscale = inv2; g.rowscale = inv1; g.rowmax = nullptr; g.n_valid = PP; g.scale_ld = l.scale_ld;
-  if ((rc = launch_gemm(256, EPI_F32, ACT_NONE, ta, tb, tc, g, s))) return rc;
+  if ((rc = launch_gemm(256, EPI_F32, ACT_NONE, false, ta, tb, tc, g, s))) return rc;
   return launch_flow_rows(sim, l.sim_ld, rows, P, window, soft, 0.f, flow, argmax, s);
 }
 

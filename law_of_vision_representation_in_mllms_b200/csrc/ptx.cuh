@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -208,6 +209,12 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uin
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32:
 //   [4,6) c_format=1 (F32)  [7,10) a_format=1 (BF16)  [10,13) b_format=1 (BF16)
 //   [15] a_major (0=K,1=MN) [16] b_major  [17,23) N>>3  [24,29) M>>4
+// 16-bit operand format of kind::f16: a_format/b_format 0 = F16, 1 = BF16 (both with fp32 accumulation, same rate).
+__host__ __device__ constexpr uint32_t make_idesc_16(int M, int N, int a_mn_major, int b_mn_major, bool f16) {
+  return (1u << 4) | ((f16 ? 0u : 1u) << 7) | ((f16 ? 0u : 1u) << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
+         (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
+         (static_cast<uint32_t>(M >> 4) << 24);
+}
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
          (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
@@ -218,6 +225,26 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+// operand-format-generic helpers: F16 = IEEE half operands, else bfloat16
+template <bool F16>
+__device__ __forceinline__ uint32_t pack16x2(float lo, float hi) {
+  if constexpr (F16) return pack_f16x2(lo, hi);
+  else return pack_bf16x2(lo, hi);
+}
+template <bool F16>
+__device__ __forceinline__ float2 unpack16x2(uint32_t w) {
+  if constexpr (F16) return __half22float2(*reinterpret_cast<const __half2*>(&w));
+  else return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+}
+template <bool F16>
+__device__ __forceinline__ float load16(const void* base, size_t idx) {
+  if constexpr (F16) return __half2float(reinterpret_cast<const __half*>(base)[idx]);
+  else return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[idx]);
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");

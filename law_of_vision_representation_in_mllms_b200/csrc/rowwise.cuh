@@ -18,8 +18,8 @@ __device__ __forceinline__ float load_as_float(const void* base, size_t idx, int
 
 // pixels [N,3,R,R] (dt) -> cols [N*G*G, Kpad] bf16, k = c*P*P + py*P + px (conv-weight flatten order),
 // zero for k >= 3*P*P.  Reference arithmetic: the stride-P conv of HF *Embeddings (Appendix A).
-__global__ void im2col_kernel(const void* __restrict__ pixels, int dt, __nv_bfloat16* __restrict__ cols, int n_img,
-                              int R, int P, int G, int Kpad) {
+__global__ void im2col_kernel(const void* __restrict__ pixels, int dt, uint16_t* __restrict__ cols, int n_img,
+                              int R, int P, int G, int Kpad, int f16) {
   const size_t total = static_cast<size_t>(n_img) * G * G * Kpad;
   const int K = 3 * P * P;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -36,7 +36,7 @@ __global__ void im2col_kernel(const void* __restrict__ pixels, int dt, __nv_bflo
       const int px = k % P;
       v = load_as_float(pixels, ((n * 3 + c) * R + (gy * P + py)) * static_cast<size_t>(R) + gx * P + px, dt);
     }
-    cols[i] = __float2bfloat16(v);
+    cols[i] = f16 ? __half_as_ushort(__float2half_rn(v)) : __bfloat16_as_ushort(__float2bfloat16(v));
   }
 }
 
@@ -102,9 +102,9 @@ __global__ void embed_finalize_kernel(const float* __restrict__ patch, const flo
 }
 
 // y[row,:] (bf16) = LayerNorm(x[row,:]) * gamma + beta, fp32 statistics.
-template <int V4>
+template <int V4, bool F16>
 __global__ void layernorm_bf16_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
-                                      const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y,
+                                      const float* __restrict__ beta, float eps, uint16_t* __restrict__ y,
                                       size_t rows) {
   constexpr int D = V4 * 128;
   const int lane = threadIdx.x & 31;
@@ -123,8 +123,8 @@ __global__ void layernorm_bf16_kernel(const float* __restrict__ x, const float* 
 #pragma unroll
   for (int j = 0; j < V4; ++j) {
     uint2 o;
-    o.x = pack_bf16x2(v[j * 4 + 0], v[j * 4 + 1]);
-    o.y = pack_bf16x2(v[j * 4 + 2], v[j * 4 + 3]);
+    o.x = pack16x2<F16>(v[j * 4 + 0], v[j * 4 + 1]);
+    o.y = pack16x2<F16>(v[j * 4 + 2], v[j * 4 + 3]);
     reinterpret_cast<uint2*>(y + row * D)[j * 32 + lane] = o;
   }
 }

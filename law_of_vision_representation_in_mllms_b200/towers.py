@@ -34,8 +34,9 @@ DEFAULT_MAX_BATCH = int(os.environ.get("LOVR_MAX_BATCH", "64"))
 class _NativeTower:
     """One (weights, resolution) instance of the native tower: packed device weights + workspace + handle."""
 
-    def __init__(self, spec: TowerSpec, cw, device, max_batch):
+    def __init__(self, spec: TowerSpec, cw, device, max_batch, operand_dtype=torch.bfloat16):
         self.spec = spec
+        self.operand_dtype = operand_dtype
         self.device = torch.device(device)
         self.max_batch = max_batch
         self._keep = []   # device tensors referenced by raw pointers
@@ -55,9 +56,9 @@ class _NativeTower:
             hidden_size=D, intermediate_size=spec.intermediate_size, num_layers=spec.num_layers,
             num_heads=spec.num_heads, image_size=spec.image_size, patch_size=P, act=spec.act,
             has_cls=int(spec.has_cls), pre_ln=int(spec.pre_ln), layerscale=int(spec.layerscale),
-            ln_eps=spec.ln_eps, patch_k_padded=kpad)
+            ln_eps=spec.ln_eps, patch_k_padded=kpad, operand_dtype=_lib.torch_dtype_code(operand_dtype))
         layers = (_lib.LayerWeights * spec.num_layers)()
-        bf = torch.bfloat16
+        bf = operand_dtype      # 16-bit tensor-core operand format of the weight matrices
         for i, lw in enumerate(cw["layers"]):
             L = layers[i]
             for name, dt in (("ln1_w", None), ("ln1_b", None), ("qkv_w", bf), ("qkv_b", None), ("o_w", bf),
@@ -153,6 +154,9 @@ class _B200VisionTower(nn.Module):
         self._state_dict = state_dict
         self._device = torch.device(device if device is not None else getattr(self._args, "lovr_device", "cuda"))
         self._max_batch = int(getattr(self._args, "lovr_max_batch", DEFAULT_MAX_BATCH))
+        od = getattr(self._args, "lovr_operand_dtype", os.environ.get("LOVR_OPERAND_DTYPE", "bf16"))
+        self._operand_dtype = {"bf16": torch.bfloat16, "fp16": torch.float16, "f16": torch.float16,
+                               torch.bfloat16: torch.bfloat16, torch.float16: torch.float16}[od]
         self._native.clear()
         self._instance(self._default_image_size())
         self.image_processor = self._make_image_processor()
@@ -167,7 +171,7 @@ class _B200VisionTower(nn.Module):
         if inst is None:
             spec_r = self._spec.at_resolution(image_size)     # raises like HF for fixed-resolution towers
             cw = canonical_weights(self._spec, self._state_dict, image_size=image_size)
-            inst = _NativeTower(spec_r, cw, self._device, self._max_batch)
+            inst = _NativeTower(spec_r, cw, self._device, self._max_batch, self._operand_dtype)
             self._native[image_size] = inst
         return inst
 
@@ -221,7 +225,9 @@ class _B200VisionTower(nn.Module):
 
     @property
     def dtype(self):
-        return torch.bfloat16        # compute dtype of the GEMM operands
+        """16-bit format of the tensor-core operands: bf16 (the reference's extraction dtype, extract.py:228) or
+        fp16 (the reference's eval dtype for towers, llava/model/builder.py:143); accumulation/residual are fp32."""
+        return getattr(self, "_operand_dtype", torch.bfloat16)
 
     @property
     def device(self):

@@ -24,7 +24,8 @@ def test_header_symbols_are_exported():
 def test_workspace_queries_need_no_gpu():
     L = _lib.lib()
     cfg = _lib.TowerConfig(hidden_size=1024, intermediate_size=4096, num_layers=24, num_heads=16, image_size=336,
-                           patch_size=14, act=1, has_cls=1, pre_ln=1, layerscale=0, ln_eps=1e-5, patch_k_padded=640)
+                           patch_size=14, act=1, has_cls=1, pre_ln=1, layerscale=0, ln_eps=1e-5, patch_k_padded=640,
+                           operand_dtype=_lib.DT_BF16)
     import ctypes as C
     b1 = L.lovr_tower_workspace_bytes(C.byref(cfg), 1)
     b8 = L.lovr_tower_workspace_bytes(C.byref(cfg), 8)
@@ -40,6 +41,6 @@ def test_no_cpu_fallback():
     x = torch.zeros(128, 64, dtype=torch.bfloat16)
     out = torch.zeros(128, 256)
     rc = L.lovr_gemm_bf16(_lib.ptr(x), 64, _lib.ptr(torch.zeros(256, 64, dtype=torch.bfloat16)), 64, _lib.ptr(out), 256,
-                          128, 256, 64, _lib.EPI_F32, 0, None, None, None)
+                          128, 256, 64, _lib.EPI_F32, 0, _lib.DT_BF16, None, None, None)
     assert rc in (_lib.E_UNSUPPORTED, _lib.E_CUDA)
     assert L.lovr_last_error()

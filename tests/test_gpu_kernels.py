@@ -62,6 +62,32 @@ def test_gemm_residual_epilogue(use_ls):
     assert G.rel_err(x, want) < 1e-5
 
 
+@pytest.mark.parametrize("act", [0, 1])
+def test_gemm_fp16_operands(act):
+    M, N, K = 700, 1024, 1024
+    A, W = _rand((M, K), 21, 1.0, torch.float16), _rand((N, K), 22, 0.05, torch.float16)
+    bias = _rand((N,), 23, 0.5, torch.float32)
+    got = G.gemm(A, W, _lib.EPI_BF16, act=act, bias=bias)
+    z = A.float() @ W.float().T + bias
+    want = [z, z * torch.sigmoid(1.702 * z)][act]
+    assert got.dtype == torch.float16
+    assert G.rel_err(got, want) < 4e-4          # fp16 output rounding: 2^-12 relative
+    x = _rand((M, N), 24, 2.0, torch.float32)
+    x0 = x.clone()
+    G.gemm(A, W, _lib.EPI_RESID_F32, bias=bias, C_inout=x)
+    assert G.rel_err(x, x0 + z) < 1e-5
+
+
+def test_attention_fp16_operands():
+    n, T, H = 2, 577, 16
+    qkv = _rand((n * T, 3 * H * 64), 31, 1.0, torch.float16)
+    want = _torch_attention(qkv, n, T, H)
+    for impl in (_lib.ATTN_TCGEN05, _lib.ATTN_SIMT_CHECK):
+        got = G.attention(qkv, n, T, H, impl)
+        assert got.dtype == torch.float16
+        assert G.rel_err(got, want) < 6e-4
+
+
 def test_gemm_rejects_bad_shapes():
     A, W = _rand((128, 100), 1), _rand((256, 100), 2)
     with pytest.raises(_lib.LovrError):
