@@ -21,6 +21,7 @@ EXPORTS = [
     "lovr_gemm_bf16", "lovr_layernorm_bf16", "lovr_attention", "lovr_im2col",
     "lovr_a_score_workspace_bytes", "lovr_a_score_maxcos",
     "lovr_c_score_workspace_bytes", "lovr_c_score_flow", "lovr_c_score_keypoints", "lovr_pck",
+    "lovr_cka_workspace_bytes", "lovr_cka_gram_elems", "lovr_cka_accumulate", "lovr_cka_finalize",
 ]
 
 
@@ -93,6 +94,14 @@ def lib():
     L.lovr_c_score_keypoints.argtypes = [vp, vp, i32, i64, i32, i32, vp, i32, i32, i32, f32, vp, vp, sz, vp]
     L.lovr_pck.restype = C.c_int
     L.lovr_pck.argtypes = [vp, vp, vp, vp, i64, i32, vp, vp]
+    L.lovr_cka_workspace_bytes.restype = sz
+    L.lovr_cka_workspace_bytes.argtypes = [i64, i32, i32]
+    L.lovr_cka_gram_elems.restype = sz
+    L.lovr_cka_gram_elems.argtypes = [i32, i32]
+    L.lovr_cka_accumulate.restype = C.c_int
+    L.lovr_cka_accumulate.argtypes = [vp, vp, i64, i32, i32, vp, vp, sz, vp]
+    L.lovr_cka_finalize.restype = C.c_int
+    L.lovr_cka_finalize.argtypes = [vp, C.c_double, i32, i32, vp, vp]
     _lib = L
     return L
 

@@ -15,6 +15,7 @@
 
 #include "attention.cuh"
 #include "attention_simt.cuh"
+#include "cka.cuh"
 #include "cscore.cuh"
 #include "gemm.cuh"
 #include "rowwise.cuh"
@@ -784,6 +785,89 @@ int lovr_pck(const float* pred, const float* gt, const uint8_t* visible, const f
   lovr::pck_kernel<<<static_cast<unsigned>((n_pairs + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
       pred, gt, visible, thresholds, static_cast<int>(n_pairs), K, out);
   LAUNCH_CHECK("pck_kernel");
+  return 0;
+}
+
+// ====================================================================================== linear CKA
+namespace {
+constexpr int kCkaChunk = 16384;  // rows per split: one TMEM accumulation run; partials are summed in fp64
+struct CkaLayout {
+  size_t zt, pa, pb, total, rpad;
+  int splits;
+};
+CkaLayout cka_layout(int64_t R, int Dx, int Dy) {
+  CkaLayout l{};
+  l.rpad = (static_cast<size_t>(R) + kCkaChunk - 1) / kCkaChunk * kCkaChunk;
+  l.splits = static_cast<int>(l.rpad / kCkaChunk);
+  const size_t Dz = static_cast<size_t>(Dx) + Dy;
+  size_t off = 0;
+  l.zt = off; off += align_up(Dz * l.rpad * 2, 1024);
+  l.pa = off; off += align_up(static_cast<size_t>(l.splits) * Dx * Dz * 4, 1024);
+  l.pb = off; off += align_up(static_cast<size_t>(l.splits) * Dy * Dy * 4, 1024);
+  l.total = off;
+  return l;
+}
+}  // namespace
+
+size_t lovr_cka_workspace_bytes(int64_t rows, int32_t Dx, int32_t Dy) { return cka_layout(rows, Dx, Dy).total; }
+size_t lovr_cka_gram_elems(int32_t Dx, int32_t Dy) {
+  return static_cast<size_t>(Dx) * (Dx + Dy) + static_cast<size_t>(Dy) * Dy + Dx + Dy;
+}
+
+int lovr_cka_accumulate(const void* X, const void* Y, int64_t rows, int32_t Dx, int32_t Dy, double* gram, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  using namespace lovr;
+  if (int rc = require_device()) return rc;
+  if (!X || !Y || !gram || !workspace) return fail(LOVR_E_ARG, "cka: null pointer");
+  if (rows <= 0) return 0;
+  if (Dx % 256 || Dy % 256) return fail(LOVR_E_ARG, "cka: feature widths must be multiples of 256 (got %d, %d)", Dx, Dy);
+  const CkaLayout l = cka_layout(rows, Dx, Dy);
+  if (workspace_bytes < l.total) return fail(LOVR_E_NOMEM, "cka workspace %zu < %zu", workspace_bytes, l.total);
+  if (reinterpret_cast<uintptr_t>(workspace) & 1023) return fail(LOVR_E_ARG, "workspace must be 1024-byte aligned");
+  if (l.rpad / kCkaRowsPerBlock > 65535) return fail(LOVR_E_ARG, "cka: at most %d rows per call", 65535 * kCkaRowsPerBlock);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  auto base = static_cast<uint8_t*>(workspace);
+  auto zt = reinterpret_cast<uint16_t*>(base + l.zt);
+  float* pa = reinterpret_cast<float*>(base + l.pa);
+  float* pb = reinterpret_cast<float*>(base + l.pb);
+  const int Dz = Dx + Dy;
+  const size_t na = static_cast<size_t>(Dx) * Dz, nb = static_cast<size_t>(Dy) * Dy;
+  double* colsum = gram + na + nb;
+  transpose_colsum_kernel<<<dim3(Dx / 64, static_cast<unsigned>(l.rpad / kCkaRowsPerBlock)), 256, 0, s>>>(
+      static_cast<const uint16_t*>(X), rows, Dx, zt, l.rpad, 0, colsum);
+  LAUNCH_CHECK("transpose_colsum_kernel");
+  transpose_colsum_kernel<<<dim3(Dy / 64, static_cast<unsigned>(l.rpad / kCkaRowsPerBlock)), 256, 0, s>>>(
+      static_cast<const uint16_t*>(Y), rows, Dy, zt, l.rpad, Dx, colsum);
+  LAUNCH_CHECK("transpose_colsum_kernel");
+  int rc;
+  for (int part = 0; part < 2; ++part) {
+    const int M = part == 0 ? Dx : Dy, N = part == 0 ? Dz : Dy;
+    const uint16_t* a_ptr = part == 0 ? zt : zt + static_cast<size_t>(Dx) * l.rpad;
+    float* c_ptr = part == 0 ? pa : pb;
+    CUtensorMap ta, tb, tc;
+    if ((rc = make_tmap(&ta, a_ptr, 2, kCkaChunk, M, l.splits, l.rpad, kCkaChunk, 64, kBM))) return rc;
+    if ((rc = make_tmap(&tb, a_ptr, 2, kCkaChunk, N, l.splits, l.rpad, kCkaChunk, 64, 256))) return rc;
+    if ((rc = make_tmap(&tc, c_ptr, 4, N, M, l.splits, N, static_cast<uint64_t>(M) * N, 32, 32))) return rc;
+    GemmArgs g{};
+    g.M = M; g.N = N; g.K = kCkaChunk; g.batch = l.splits; g.n_inner = 1;
+    g.bias = nullptr; g.colscale = nullptr; g.rowscale = nullptr; g.rowmax = nullptr; g.n_valid = N; g.scale_ld = 0;
+    if ((rc = launch_gemm(256, EPI_F32, ACT_NONE, false, ta, tb, tc, g, s))) return rc;
+    const size_t n = static_cast<size_t>(M) * N;
+    reduce_partials_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(c_ptr, n, l.splits, n,
+                                                                                  part == 0 ? gram : gram + na);
+    LAUNCH_CHECK("reduce_partials_kernel");
+  }
+  return 0;
+}
+
+int lovr_cka_finalize(const double* gram, double n_rows, int32_t Dx, int32_t Dy, double* out3, void* stream) {
+  if (int rc = require_device()) return rc;
+  if (!gram || !out3) return fail(LOVR_E_ARG, "cka_finalize: null pointer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(cudaMemsetAsync(out3, 0, 3 * sizeof(double), s));
+  const size_t na = static_cast<size_t>(Dx) * (Dx + Dy), nb = static_cast<size_t>(Dy) * Dy;
+  lovr::cka_finalize_kernel<<<296, 256, 0, s>>>(gram, gram + na, gram + na + nb, n_rows, Dx, Dy, out3);
+  LAUNCH_CHECK("cka_finalize_kernel");
   return 0;
 }
 
