@@ -32,7 +32,7 @@ def test_cka_shards_add_up_and_identity():
     full = K.linear_cka(X.cuda(), Y.cuda())
     gram, n1, Dx, Dy = K.cka_gram(X[:11000].cuda(), Y[:11000].cuda())
     gram, n2, _, _ = K.cka_gram(X[11000:].cuda(), Y[11000:].cuda(), gram)        # second shard adds into the same sums
-    assert abs(K.cka_from_gram(gram, n1 + n2, Dx, Dy) - full) < 1e-9
+    assert abs(K.cka_from_gram(gram, n1 + n2, Dx, Dy) - full) < 2e-6      # different split boundaries, fp32 partials
     assert abs(K.linear_cka(X.cuda(), X.cuda()) - 1.0) < 1e-6
     feats = X.reshape(50, 600, 256)                                             # [N, P, D] layout is flattened
     assert abs(K.linear_cka(feats.cuda(), Y.reshape(50, 600, 256).cuda()) - full) < 1e-12
