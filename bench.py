@@ -142,7 +142,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from law_of_vision_representation_in_mllms_b200 import _lib, a_score as A, extract as X
+    from law_of_vision_representation_in_mllms_b200 import _lib, a_score as A, c_score as CS, cka as CK, extract as X
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback); use --impl reference for the CPU leg")
@@ -232,7 +232,41 @@ def main():
             dist.all_reduce(a_ms, op=dist.ReduceOp.MAX)
         a_info = dict(config="A-score max-cos over 10k x 576 x 1024 bf16 pairs (configs[2])", seconds=a_ms.item() / 1e3,
                       mean_a=s.item() / n_pairs, hbm_gbs=2 * n_pairs * T_PATCH * D * 2 / (a_ms.item() / 1e3) / 1e9 / world)
-        del o, r_
+        # ---- linear CKA over the same rows (north_star metric; builder-defined): per-shard Gram, one all-reduce
+        CK.linear_cka(o[:8], r_[:8])
+        barrier()
+        e0.record()
+        gram, nrows, dx, dy = CK.cka_gram(o, r_)
+        nt = torch.tensor([float(nrows)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(gram)
+            dist.all_reduce(nt)
+        cka_val = CK.cka_from_gram(gram, nt.item(), dx, dy)
+        e1.record()
+        barrier()
+        c_ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(c_ms, op=dist.ReduceOp.MAX)
+        a_info["linear_cka"] = dict(seconds=c_ms.item() / 1e3, value=cka_val, rows=n_pairs * T_PATCH,
+                                    tflops=2.0 * n_pairs * T_PATCH * (D * 2 * D + D * D) / (c_ms.item() / 1e3) / 1e12 / world)
+        del o, r_, gram
+        # ---- C score at the C5 shape: SPair-shaped P=60, D=1024 pairs (bf16 descriptors), sharded like the images
+        g5 = torch.Generator(device=dev).manual_seed(2000 + rank)
+        npairs_dense, npairs_kp, Pg, K = 32, 512, 60, 12
+        d1 = torch.randn(npairs_kp, Pg * Pg, D, generator=g5, device=dev).to(torch.bfloat16)
+        d2 = torch.randn(npairs_kp, Pg * Pg, D, generator=g5, device=dev).to(torch.bfloat16)
+        idx = torch.randint(0, Pg * Pg, (npairs_kp, K), generator=g5, device=dev).cpu().numpy()
+        CS.get_flow(d1[:2], d2[:2]); CS.keypoint_transformation(d1[:2], d2[:2], idx[:2])
+        barrier()
+        e0.record(); CS.get_flow(d1[:npairs_dense], d2[:npairs_dense]); e1.record(); barrier()
+        dense_ms = e0.elapsed_time(e1)
+        e0.record(); CS.keypoint_transformation(d1, d2, idx); e1.record(); barrier()
+        kp_ms = e0.elapsed_time(e1)
+        a_info["c_score"] = dict(config="C-score P=60 D=1024 bf16 pairs (configs[4] shape), per GPU",
+                                 dense_flow_us_per_pair=1e3 * dense_ms / npairs_dense,
+                                 dense_tflops=2.0 * Pg ** 4 * D * npairs_dense / (dense_ms / 1e3) / 1e12,
+                                 keypoint_path_us_per_pair=1e3 * kp_ms / npairs_kp)
+        del d1, d2
 
     if rank == 0:
         peaks = measured_peaks()

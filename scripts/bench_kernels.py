@@ -53,6 +53,8 @@ def main():
     res.append(dict(kernel="torch_matmul_fc1_shape(cuBLAS)", ms=ms, tflops=2 * M * D * I / ms / 1e9))
     ms = timeit(lambda: G.attention(qkv, n_img, T, H, _lib.ATTN_TCGEN05))
     res.append(dict(kernel="attention_tcgen05", ms=ms, tflops=4 * n_img * H * T * T * 64 / ms / 1e9))
+    ms = timeit(lambda: G.attention(qkv, n_img, T, H, _lib.ATTN_TCGEN05_V2))
+    res.append(dict(kernel="attention2_tcgen05", ms=ms, tflops=4 * n_img * H * T * T * 64 / ms / 1e9))
     g, b = torch.ones(D, device=dev), torch.zeros(D, device=dev)
     ms = timeit(lambda: G.layernorm(x, g, b, 1e-5))
     res.append(dict(kernel="layernorm", ms=ms, gbs=M * D * 6 / ms / 1e6))
