@@ -25,6 +25,7 @@ struct AttnArgs {
   int last_w;   // width of the last KV block, multiple of 32
   float scale;  // head_dim^-0.5
   uint16_t* out;  // [N*T, H*64], 16-bit operand format
+  int debug;      // timing experiments only (LOVR_ATTN_DEBUG): 1 = skip pass 1, 2 = no ex2, 4 = skip max/exp math
 };
 
 inline size_t attn_smem_bytes(int nb) {

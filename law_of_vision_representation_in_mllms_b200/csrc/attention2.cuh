@@ -157,9 +157,13 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
       for (int t = g; t < q_tiles; t += 2, ++k) {
         mbar_wait(q_full(g), k & 1);
         // ---- pass 1: S double-buffered; buffer 1 aliases O of the previous tile -> wait for its epilogue
-        for (int j = 0; j < nb; ++j) {
-          if (j == 1) mbar_wait(o_empty(g), (k & 1) ^ 1);
-          issue_qk(j & 1, j);
+        if (p.debug & 1) {
+          mbar_wait(o_empty(g), (k & 1) ^ 1);
+        } else {
+          for (int j = 0; j < nb; ++j) {
+            if (j == 1) mbar_wait(o_empty(g), (k & 1) ^ 1);
+            issue_qk(j & 1, j);
+          }
         }
         // ---- pass 2
         if (k == 0) mbar_wait(v_full, 0);
@@ -193,8 +197,8 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
     int k = 0;
     for (int t = g; t < q_tiles; t += 2, ++k) {
       // ---------------- pass 1: exact row maximum of the raw scores
-      float m = -INFINITY;
-      for (int j = 0; j < nb; ++j) {
+      float m0 = (p.debug & 1) ? 0.f : -INFINITY, m1 = m0, m2 = m0, m3 = m0;
+      for (int j = 0; j < ((p.debug & 1) ? 0 : nb); ++j) {
         const int b = j & 1;
         mbar_wait(s_full(g, b), cs[b] & 1);
         tc_fence_after();
@@ -207,9 +211,19 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
           if (c < nch) {
             tmem_ld_wait_dep(buf[c & 1]);
             if (c + 1 < nch) tmem_ld_32x32b_x32(tS[b] + (c + 1) * 32, buf[(c + 1) & 1]);
+            if (c * 32 + 32 <= valid) {  // warp-uniform: no per-element masking away from the sequence tail
 #pragma unroll
-            for (int e = 0; e < 32; ++e)
-              if (c * 32 + e < valid) m = fmaxf(m, __uint_as_float(buf[c & 1][e]));
+              for (int e = 0; e < 32; e += 4) {  // four independent chains instead of one 4-cycle-latency chain
+                m0 = fmaxf(m0, __uint_as_float(buf[c & 1][e]));
+                m1 = fmaxf(m1, __uint_as_float(buf[c & 1][e + 1]));
+                m2 = fmaxf(m2, __uint_as_float(buf[c & 1][e + 2]));
+                m3 = fmaxf(m3, __uint_as_float(buf[c & 1][e + 3]));
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 32; ++e)
+                if (c * 32 + e < valid) m0 = fmaxf(m0, __uint_as_float(buf[c & 1][e]));
+            }
           }
         }
         tc_fence_before();
@@ -217,9 +231,9 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
         if (lane == 0) mbar_arrive(s_empty(g, b));
         ++cs[b];
       }
-      const float mc = m * c1;
+      const float mc = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * c1;
       // ---------------- pass 2: P = exp2(s*c1 - m*c1) in 64-column halves, row sum
-      float l = 0.f;
+      float l0 = 0.f, l1 = 0.f;
       for (int j = 0; j < nb; ++j) {
         mbar_wait(s_full(g, 0), cs[0] & 1);
         tc_fence_after();
@@ -240,14 +254,27 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
               __syncwarp();
               if (lane == 0) mbar_arrive(s_empty(g, 0));
             }
+            if (c * 32 + 32 <= valid) {  // warp-uniform fast path: FFMA + MUFU.EX2 + FADD + half a pack per element
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              float e0 = ex2_approx(fmaf(__uint_as_float(buf[c & 1][i]), c1, -mc));
-              float e1 = ex2_approx(fmaf(__uint_as_float(buf[c & 1][i + 1]), c1, -mc));
-              e0 = (c * 32 + i < valid) ? e0 : 0.f;
-              e1 = (c * 32 + i + 1 < valid) ? e1 : 0.f;
-              l += e0 + e1;
-              pk[(c & 1) * 16 + (i >> 1)] = pack16x2<F16>(e0, e1);
+              for (int i = 0; i < 32; i += 2) {
+                float e0 = fmaf(__uint_as_float(buf[c & 1][i]), c1, -mc);
+                float e1 = fmaf(__uint_as_float(buf[c & 1][i + 1]), c1, -mc);
+                if (!(p.debug & 2)) { e0 = ex2_approx(e0); e1 = ex2_approx(e1); }
+                l0 += e0;
+                l1 += e1;
+                pk[(c & 1) * 16 + (i >> 1)] = pack16x2<F16>(e0, e1);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                float e0 = ex2_approx(fmaf(__uint_as_float(buf[c & 1][i]), c1, -mc));
+                float e1 = ex2_approx(fmaf(__uint_as_float(buf[c & 1][i + 1]), c1, -mc));
+                e0 = (c * 32 + i < valid) ? e0 : 0.f;
+                e1 = (c * 32 + i + 1 < valid) ? e1 : 0.f;
+                l0 += e0;
+                l1 += e1;
+                pk[(c & 1) * 16 + (i >> 1)] = pack16x2<F16>(e0, e1);
+              }
             }
             if ((c & 1) == 1 || c == nch - 1) {  // a half is complete -> hand it to the P·V issuer
               mbar_wait(p_empty(g), (cp & 1) ^ 1);
@@ -277,7 +304,7 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
       if (lane == 0) mbar_arrive(o_empty(g));
       const int tok = t * 128 + r;
       if (tok < p.T) {
-        const float inv = 1.0f / l;
+        const float inv = 1.0f / (l0 + l1);
         uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<size_t>(n) * p.T + tok) * D + h * 64);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {

@@ -7,6 +7,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -294,6 +295,10 @@ int launch_attention(const void* qkv, void* out, int n_img, int T, int H, int im
   lovr::AttnArgs a{};
   a.T = T; a.H = H; a.nb = nb; a.last_w = (rem + 31) / 32 * 32; a.scale = 0.125f;
   a.out = static_cast<uint16_t*>(out);
+  {
+    const char* dbg = getenv("LOVR_ATTN_DEBUG");
+    a.debug = dbg ? atoi(dbg) : 0;
+  }
   CUtensorMap tq;
   int rc;
   if ((rc = make_tmap(&tq, qkv, 2, 3 * D, T, n_img, 3 * D, static_cast<uint64_t>(3) * D * T, 64, 128))) return rc;
