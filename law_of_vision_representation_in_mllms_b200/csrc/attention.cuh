@@ -23,6 +23,8 @@ struct AttnArgs {
   int H;        // heads
   int nb;       // ceil(T / 128)
   int last_w;   // width of the last KV block, multiple of 32
+  int nu;       // (second-generation kernel) ceil(T / 64) KV units
+  int last_w64; // width of the last 64-column unit: 32 or 64
   float scale;  // head_dim^-0.5
   uint16_t* out;  // [N*T, H*64], 16-bit operand format
   int debug;      // timing experiments only (LOVR_ATTN_DEBUG): 1 = skip pass 1, 2 = no ex2, 4 = skip max/exp math

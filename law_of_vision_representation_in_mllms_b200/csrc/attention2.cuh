@@ -1,27 +1,31 @@
-// Fused non-causal ViT attention on tcgen05, second generation: TWO independent softmax pipelines per CTA.
+// Fused non-causal ViT attention on tcgen05, second generation.
 //
-// One CTA per (image, head); K and V of the head stay resident in shared memory.  Query tiles of 128 rows alternate
-// between two warpgroup pipelines (tile t -> pipeline t & 1); each pipeline has its own Q buffer, P buffer, TMEM
-// region, mbarriers and its own single-thread tcgen05.mma issuer, so the tensor-core round trips, mbarrier wake-ups
-// and the MUFU-bound exp work of one pipeline overlap with the other's (the first-generation kernel, one pipeline,
-// was latency-bound: XU pipe 26 %, tensor pipe 19 %).
+// Measured facts that shape it (B200, scripts/micro/tmem_bw.cu and profiles/): tcgen05.ld moves ~64 B/cycle per SM
+// regardless of how many warps issue it, and one x32 load has ~250-300 cycles of latency under load.  With head_dim 64
+// the score tile S (fp32, 4 B per element) is therefore the bottleneck resource: the first-generation kernel read every
+// S element twice (max pass + exp pass: 3.4 MB of TMEM reads per (image, head) = 52k of its 88k cycles).  This kernel
+// reads S exactly once:
+//   * single-pass ONLINE softmax over 64-column KV units, thread = query row;
+//   * the running row maximum is only advanced when a unit exceeds it by more than 2^8 (exp2 domain), so the O
+//     accumulator in TMEM is rescaled (tcgen05.ld -> scale -> tcgen05.st, by the softmax warp that owns the rows) only
+//     on the rare units where that happens; P values are then bounded by 2^8 and the final O / l is exact;
+//   * TWO independent pipelines per CTA (query tile t -> pipeline t & 1), each with its own Q/P smem, TMEM region
+//     (S_a, S_b double-buffered 64-column units + O), mbarriers and single-thread MMA issuer, so TMEM-load latency,
+//     mbarrier wake-ups and MMA round trips of one pipeline hide behind the other.
 //
-//   warp 0        TMA: K blocks, V blocks, Q tiles of both pipelines
-//   warp 1 / 2    MMA issuer of pipeline 0 / 1 (one thread each); warp 1 also owns TMEM alloc/dealloc
-//   warps 3-6     softmax of pipeline 0 (thread = query row via tcgen05.ld 32x32b)
-//   warps 7-10    softmax of pipeline 1
-//
-// Per pipeline, TMEM columns [g*256, g*256+256): S0 = +0..127, S1 = +128..255, O = +128..191 (aliases S1).
-//   pass 1 (exact row max): S double-buffered (S0/S1) — only max is taken, so the QK^T latency must be hidden
-//   pass 2 (P = exp2((s-m)*scale*log2e), O += P·V): S single-buffered in S0 (exp-bound), O accumulates in +128..191;
-//           P goes through one 16 KB swizzled smem atom per pipeline in 64-column halves.
-// Two-pass softmax needs no accumulator rescaling; the doubled QK^T MMAs are free in a MUFU-bound kernel.
+//   warp 0        TMA: K blocks, V blocks (resident for the whole CTA), Q tiles of both pipelines
+//   warp 1 / 2    tcgen05.mma issuer of pipeline 0 / 1;  S_u = Q·K_u^T (K-major x K-major, N = 64),
+//                 O += P_u·V_u (P from smem K-major, V as MN-major B operand: no transpose of V anywhere)
+//   warps 4-7     softmax of pipeline 0      warps 8-11   softmax of pipeline 1   (warp 3 idle)
+// Registers are rebalanced with setmaxnreg: the control warpgroup drops to 56, the softmax warpgroups rise to 224.
+// TMEM columns of pipeline g: [g*256 + 0, +64) S_a, [+64, +128) S_b, [+128, +192) O.
 #pragma once
 #include "attention.cuh"
 
 namespace lovr {
 
-constexpr int kAttn2Threads = 11 * 32;
+constexpr int kAttn2Threads = 12 * 32;  // warpgroup 0: TMA + 2 MMA issuers (+1 idle warp); warpgroups 1,2: softmax
+constexpr float kAttnRescaleLog2 = 8.0f;
 
 inline size_t attn2_smem_bytes(int nb) { return static_cast<size_t>(2 * nb + 2 + 2) * 16384 + 512 + 1024; }
 
@@ -38,7 +42,6 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * 16384);
   uint64_t* k_full = bars + 0;
   uint64_t* v_full = bars + 1;
-  // per pipeline g: 10 barriers starting at bars + 2 + 10*g
   auto q_full = [&](int g) { return bars + 2 + 10 * g + 0; };
   auto q_empty = [&](int g) { return bars + 2 + 10 * g + 1; };
   auto s_full = [&](int g, int b) { return bars + 2 + 10 * g + 2 + b; };
@@ -53,7 +56,8 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
   const int n = blockIdx.x / p.H, h = blockIdx.x % p.H;
   const int D = p.H * 64;
   const int q_tiles = (p.T + 127) / 128;
-  auto width_of = [&](int j) { return (j == nb - 1) ? p.last_w : 128; };
+  const int nu = p.nu;  // 64-column KV units
+  auto width_of = [&](int u) { return (u == nu - 1) ? p.last_w64 : 64; };
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQKV);
@@ -82,6 +86,8 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
     // ===================================================================== TMA
     if (lane == 0) {
@@ -105,8 +111,7 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
           const int t = 2 * next_k[g] + g;
           if (t >= q_tiles) continue;
           pending = true;
-          // the (next_k-1)-th use of the buffer has been released when q_empty completed next_k times
-          if (mbar_try_wait(q_empty(g), (next_k[g] - 1) & 1)) {
+          if (mbar_try_wait(q_empty(g), (next_k[g] - 1) & 1)) {  // previous tile's QK^T all retired
             mbar_arrive_expect_tx(q_full(g), 16384);
             tma_load_3d(sQ + g * 16384, &tmQKV, q_full(g), h * 64, t * 128, n);
             ++next_k[g];
@@ -123,17 +128,18 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
     // ===================================================================== MMA issuer of pipeline g
     if (lane == 0) {
       const int g = warp - 1;
-      const uint32_t tS[2] = {tmem_base + g * 256, tmem_base + g * 256 + 128};
+      const uint32_t tS[2] = {tmem_base + g * 256, tmem_base + g * 256 + 64};
       const uint32_t tO = tmem_base + g * 256 + 128;
       const uint32_t qa = smem_u32(sQ + g * 16384), pa = smem_u32(sP + g * 16384);
       const uint32_t idesc_o = make_idesc_16(128, 64, 0, 1, F16);  // B (=V) is MN-major
       uint32_t us[2] = {0, 0};  // fills issued per S buffer
-      uint32_t up = 0;          // P halves consumed
-      auto issue_qk = [&](int b, int j) {
+      uint32_t up = 0;          // P units consumed
+      auto issue_qk = [&](int u) {
+        const int b = u & 1;
         mbar_wait(s_empty(g, b), (us[b] & 1) ^ 1);
         tc_fence_after();
-        const uint32_t ka = smem_u32(sK + j * 16384);
-        const uint32_t idesc = make_idesc_16(128, width_of(j), 0, 0, F16);
+        const uint32_t ka = smem_u32(sK + (u >> 1) * 16384) + (u & 1) * 8192;
+        const uint32_t idesc = make_idesc_16(128, width_of(u), 0, 0, F16);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_bf16_ss(tS[b], make_smem_desc_sw128(qa + k * 32, 16, 1024), make_smem_desc_sw128(ka + k * 32, 16, 1024),
@@ -141,14 +147,14 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
         umma_commit(s_full(g, b));
         ++us[b];
       };
-      auto issue_pv = [&](int j, int half, bool first) {
+      auto issue_pv = [&](int u) {
         mbar_wait(p_full(g), up & 1);
         tc_fence_after();
-        const int cols = min(64, width_of(j) - 64 * half);
-        const uint32_t va = smem_u32(sV + j * 16384) + half * 8192;
-        for (int s = 0; s < cols / 16; ++s)
+        const uint32_t va = smem_u32(sV + (u >> 1) * 16384) + (u & 1) * 8192;
+        const int steps = width_of(u) / 16;
+        for (int s = 0; s < steps; ++s)
           umma_bf16_ss(tO, make_smem_desc_sw128(pa + s * 32, 16, 1024), make_smem_desc_sw128(va + s * 2048, 16384, 1024),
-                       idesc_o, (first && s == 0) ? 0u : 1u);
+                       idesc_o, (u == 0 && s == 0) ? 0u : 1u);
         umma_commit(p_empty(g));
         ++up;
       };
@@ -156,141 +162,146 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
       int k = 0;
       for (int t = g; t < q_tiles; t += 2, ++k) {
         mbar_wait(q_full(g), k & 1);
-        // ---- pass 1: S double-buffered; buffer 1 aliases O of the previous tile -> wait for its epilogue
-        if (p.debug & 1) {
-          mbar_wait(o_empty(g), (k & 1) ^ 1);
-        } else {
-          for (int j = 0; j < nb; ++j) {
-            if (j == 1) mbar_wait(o_empty(g), (k & 1) ^ 1);
-            issue_qk(j & 1, j);
-          }
-        }
-        // ---- pass 2
+        int issued = 0;
+        issue_qk(issued++);
+        if (nu > 1) issue_qk(issued++);
+        if (issued == nu) umma_commit(q_empty(g));
         if (k == 0) mbar_wait(v_full, 0);
-        issue_qk(0, 0);
-        // O aliases S1: every pass-1 read of S1 must be complete before the first P·V lands there
-        mbar_wait(s_empty(g, 1), (us[1] & 1) ^ 1);
-        if (nb == 1) mbar_wait(o_empty(g), (k & 1) ^ 1);  // (no pass-1 use of S1 happened: still wait for the epilogue)
+        mbar_wait(o_empty(g), (k & 1) ^ 1);  // epilogue of this pipeline's previous tile has read O
         tc_fence_after();
-        for (int j = 0; j < nb; ++j) {
-          issue_pv(j, 0, j == 0);
-          if (j + 1 < nb) issue_qk(0, j + 1);
-          else umma_commit(q_empty(g));  // all QK^T of this tile issued: Q buffer reusable when they retire
-          if (width_of(j) > 64) issue_pv(j, 1, false);
+        for (int u = 0; u < nu; ++u) {
+          issue_pv(u);
+          if (issued < nu) {
+            issue_qk(issued++);
+            if (issued == nu) umma_commit(q_empty(g));  // every QK^T of this tile issued: Q reusable when they retire
+          }
         }
         umma_commit(o_full(g));
       }
     }
+  }
   } else {
     // ===================================================================== softmax pipelines
-    const int g = (warp - 3) >> 2;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    const int g = (warp - 4) >> 2;
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
     const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t tS[2] = {tmem_base + g * 256 + lane_sel, tmem_base + g * 256 + 128 + lane_sel};
+    const uint32_t tS[2] = {tmem_base + g * 256 + lane_sel, tmem_base + g * 256 + 64 + lane_sel};
     const uint32_t tO = tmem_base + g * 256 + 128 + lane_sel;
     const uint32_t p_row = smem_u32(sP + g * 16384) + r * 128;
     const uint32_t row_sw = r & 7;
     const float c1 = p.scale * 1.4426950408889634f;
     uint32_t cs[2] = {0, 0};  // S fills consumed per buffer
-    uint32_t cp = 0;          // P halves produced
+    uint32_t cp = 0;          // P units produced
     int k = 0;
     for (int t = g; t < q_tiles; t += 2, ++k) {
-      // ---------------- pass 1: exact row maximum of the raw scores
-      float m0 = (p.debug & 1) ? 0.f : -INFINITY, m1 = m0, m2 = m0, m3 = m0;
-      for (int j = 0; j < ((p.debug & 1) ? 0 : nb); ++j) {
-        const int b = j & 1;
+      float m_used = 0.f;  // row maximum (raw score units) the exponentials are currently taken against
+      float l0 = 0.f, l1 = 0.f;
+      for (int u = 0; u < nu; ++u) {
+        const int b = u & 1;
+        const int w = width_of(u);
+        const int valid = min(64, p.T - u * 64);
         mbar_wait(s_full(g, b), cs[b] & 1);
         tc_fence_after();
-        const int nch = width_of(j) >> 5;
-        const int valid = min(128, p.T - j * 128);
         uint32_t buf[2][32];
         tmem_ld_32x32b_x32(tS[b], buf[0]);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          if (c < nch) {
-            tmem_ld_wait_dep(buf[c & 1]);
-            if (c + 1 < nch) tmem_ld_32x32b_x32(tS[b] + (c + 1) * 32, buf[(c + 1) & 1]);
-            if (c * 32 + 32 <= valid) {  // warp-uniform: no per-element masking away from the sequence tail
-#pragma unroll
-              for (int e = 0; e < 32; e += 4) {  // four independent chains instead of one 4-cycle-latency chain
-                m0 = fmaxf(m0, __uint_as_float(buf[c & 1][e]));
-                m1 = fmaxf(m1, __uint_as_float(buf[c & 1][e + 1]));
-                m2 = fmaxf(m2, __uint_as_float(buf[c & 1][e + 2]));
-                m3 = fmaxf(m3, __uint_as_float(buf[c & 1][e + 3]));
-              }
-            } else {
-#pragma unroll
-              for (int e = 0; e < 32; ++e)
-                if (c * 32 + e < valid) m0 = fmaxf(m0, __uint_as_float(buf[c & 1][e]));
-            }
-          }
-        }
+        if (w == 64) tmem_ld_32x32b_x32(tS[b] + 32, buf[1]);
+        tmem_ld_wait_dep(buf[0]);
+        if (w == 64) tmem_ld_wait_dep(buf[1]);
+        // S unit is in registers: give the buffer back so the next-but-one QK^T can start
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(s_empty(g, b));
         ++cs[b];
-      }
-      const float mc = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * c1;
-      // ---------------- pass 2: P = exp2(s*c1 - m*c1) in 64-column halves, row sum
-      float l0 = 0.f, l1 = 0.f;
-      for (int j = 0; j < nb; ++j) {
-        mbar_wait(s_full(g, 0), cs[0] & 1);
-        tc_fence_after();
-        const int nch = width_of(j) >> 5;
-        const int valid = min(128, p.T - j * 128);
-        uint32_t buf[2][32];
-        uint32_t pk[32];  // one 64-column half, packed 16-bit pairs
-        tmem_ld_32x32b_x32(tS[0], buf[0]);
+        // ---- unit maximum
+        float hm;
+        if (valid == 64) {
+          float a0 = -INFINITY, a1 = a0, a2 = a0, a3 = a0;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          if (c < nch) {
-            tmem_ld_wait_dep(buf[c & 1]);
-            if (c + 1 < nch) {
-              tmem_ld_32x32b_x32(tS[0] + (c + 1) * 32, buf[(c + 1) & 1]);
-            } else {
-              // every TMEM read of this S block has completed: release it so the next QK^T overlaps the exps
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(s_empty(g, 0));
+          for (int e = 0; e < 32; e += 4) {
+            a0 = fmaxf(a0, fmaxf(__uint_as_float(buf[0][e]), __uint_as_float(buf[1][e])));
+            a1 = fmaxf(a1, fmaxf(__uint_as_float(buf[0][e + 1]), __uint_as_float(buf[1][e + 1])));
+            a2 = fmaxf(a2, fmaxf(__uint_as_float(buf[0][e + 2]), __uint_as_float(buf[1][e + 2])));
+            a3 = fmaxf(a3, fmaxf(__uint_as_float(buf[0][e + 3]), __uint_as_float(buf[1][e + 3])));
+          }
+          hm = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+        } else {
+          hm = -INFINITY;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            if (e < valid) hm = fmaxf(hm, __uint_as_float(buf[0][e]));
+            if (w == 64 && 32 + e < valid) hm = fmaxf(hm, __uint_as_float(buf[1][e]));
+          }
+        }
+        // ---- online maximum; rescale O only when the maximum moves by more than 2^kAttnRescaleLog2
+        if (u == 0) {
+          m_used = hm;
+        } else {
+          const bool need = (hm - m_used) * c1 > kAttnRescaleLog2;
+          if (__any_sync(0xffffffffu, need)) {
+            mbar_wait(p_empty(g), (cp & 1) ^ 1);  // every P·V issued so far has landed in O
+            tc_fence_after();
+            const float alpha = need ? ex2_approx((m_used - hm) * c1) : 1.0f;
+            if (need) m_used = hm;
+            l0 *= alpha;
+            l1 *= alpha;
+#pragma unroll
+            for (int piece = 0; piece < 2; ++piece) {
+              uint32_t tmp[32];
+              tmem_ld_32x32b_x32(tO + piece * 32, tmp);
+              tmem_ld_wait_dep(tmp);
+#pragma unroll
+              for (int e = 0; e < 32; ++e) tmp[e] = __float_as_uint(__uint_as_float(tmp[e]) * alpha);
+              tmem_st_32x32b_x32(tO + piece * 32, tmp);
             }
-            if (c * 32 + 32 <= valid) {  // warp-uniform fast path: FFMA + MUFU.EX2 + FADD + half a pack per element
+            tmem_st_wait();
+            tc_fence_before();
+          }
+        }
+        const float mc = m_used * c1;
+        // ---- P = exp2(s*c1 - m*c1), row sum
+        uint32_t pk[32];
+        if (valid == 64) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              float e0 = fmaf(__uint_as_float(buf[c][i]), c1, -mc);
+              float e1 = fmaf(__uint_as_float(buf[c][i + 1]), c1, -mc);
+              if (!(p.debug & 2)) { e0 = ex2_approx(e0); e1 = ex2_approx(e1); }
+              l0 += e0;
+              l1 += e1;
+              pk[c * 16 + (i >> 1)] = pack16x2<F16>(e0, e1);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            if (c * 32 < w) {
 #pragma unroll
               for (int i = 0; i < 32; i += 2) {
-                float e0 = fmaf(__uint_as_float(buf[c & 1][i]), c1, -mc);
-                float e1 = fmaf(__uint_as_float(buf[c & 1][i + 1]), c1, -mc);
-                if (!(p.debug & 2)) { e0 = ex2_approx(e0); e1 = ex2_approx(e1); }
-                l0 += e0;
-                l1 += e1;
-                pk[(c & 1) * 16 + (i >> 1)] = pack16x2<F16>(e0, e1);
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; i += 2) {
-                float e0 = ex2_approx(fmaf(__uint_as_float(buf[c & 1][i]), c1, -mc));
-                float e1 = ex2_approx(fmaf(__uint_as_float(buf[c & 1][i + 1]), c1, -mc));
+                float e0 = ex2_approx(fmaf(__uint_as_float(buf[c][i]), c1, -mc));
+                float e1 = ex2_approx(fmaf(__uint_as_float(buf[c][i + 1]), c1, -mc));
                 e0 = (c * 32 + i < valid) ? e0 : 0.f;
                 e1 = (c * 32 + i + 1 < valid) ? e1 : 0.f;
                 l0 += e0;
                 l1 += e1;
-                pk[(c & 1) * 16 + (i >> 1)] = pack16x2<F16>(e0, e1);
+                pk[c * 16 + (i >> 1)] = pack16x2<F16>(e0, e1);
               }
-            }
-            if ((c & 1) == 1 || c == nch - 1) {  // a half is complete -> hand it to the P·V issuer
-              mbar_wait(p_empty(g), (cp & 1) ^ 1);
-              const int nq = ((c & 1) == 1) ? 8 : 4;  // 16-byte chunks in this half
-#pragma unroll
-              for (int q = 0; q < 8; ++q)
-                if (q < nq)
-                  st_shared_v4(p_row + ((q ^ row_sw) << 4), pk[q * 4 + 0], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
-              fence_proxy_async_smem();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(p_full(g));
-              ++cp;
             }
           }
         }
-        ++cs[0];
+        // ---- hand the unit to the P·V issuer
+        mbar_wait(p_empty(g), (cp & 1) ^ 1);
+        const int nq = w >> 3;  // 16-byte chunks
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (q < nq) st_shared_v4(p_row + ((q ^ row_sw) << 4), pk[q * 4 + 0], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full(g));
+        ++cp;
       }
       // ---------------- O / l -> global
       mbar_wait(o_full(g), k & 1);
@@ -308,13 +319,13 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
         uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<size_t>(n) * p.T + tok) * D + h * 64);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          uint4 w;
+          uint4 w4;
           const uint32_t* src = (q < 4) ? &o0[q * 8] : &o1[(q - 4) * 8];
-          w.x = pack16x2<F16>(__uint_as_float(src[0]) * inv, __uint_as_float(src[1]) * inv);
-          w.y = pack16x2<F16>(__uint_as_float(src[2]) * inv, __uint_as_float(src[3]) * inv);
-          w.z = pack16x2<F16>(__uint_as_float(src[4]) * inv, __uint_as_float(src[5]) * inv);
-          w.w = pack16x2<F16>(__uint_as_float(src[6]) * inv, __uint_as_float(src[7]) * inv);
-          dst[q] = w;
+          w4.x = pack16x2<F16>(__uint_as_float(src[0]) * inv, __uint_as_float(src[1]) * inv);
+          w4.y = pack16x2<F16>(__uint_as_float(src[2]) * inv, __uint_as_float(src[3]) * inv);
+          w4.z = pack16x2<F16>(__uint_as_float(src[4]) * inv, __uint_as_float(src[5]) * inv);
+          w4.w = pack16x2<F16>(__uint_as_float(src[6]) * inv, __uint_as_float(src[7]) * inv);
+          dst[q] = w4;
         }
       }
     }

@@ -294,6 +294,8 @@ int launch_attention(const void* qkv, void* out, int n_img, int T, int H, int im
   const int rem = T - 128 * (nb - 1);
   lovr::AttnArgs a{};
   a.T = T; a.H = H; a.nb = nb; a.last_w = (rem + 31) / 32 * 32; a.scale = 0.125f;
+  a.nu = (T + 63) / 64;
+  a.last_w64 = (T - 64 * (a.nu - 1) + 31) / 32 * 32;
   a.out = static_cast<uint16_t*>(out);
   {
     const char* dbg = getenv("LOVR_ATTN_DEBUG");
