@@ -27,6 +27,7 @@ struct AttnArgs {
   int last_w64; // width of the last 64-column unit: 32 or 64
   float scale;  // head_dim^-0.5
   uint16_t* out;  // [N*T, H*64], 16-bit operand format
+  long long* trace;  // debug & 8: clock64 timeline of CTA 0, pipeline 0 (diagnostics only)
   int debug;      // timing experiments only (LOVR_ATTN_DEBUG): 1 = skip pass 1, 2 = no ex2, 4 = skip max/exp math
 };
 

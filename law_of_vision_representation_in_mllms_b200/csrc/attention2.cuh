@@ -29,6 +29,8 @@ constexpr float kAttnRescaleLog2 = 8.0f;
 
 inline size_t attn2_smem_bytes(int nb) { return static_cast<size_t>(2 * nb + 2 + 2) * 16384 + 512 + 1024; }
 
+#define LOVR_TRACE(cond, idx) do { if ((p.debug & 8) && blockIdx.x == 0 && (cond)) p.trace[(idx)] = clock64(); } while (0)
+
 template <bool F16>
 __global__ void __launch_bounds__(kAttn2Threads, 1)
 attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs p) {
@@ -59,6 +61,7 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
   const int nu = p.nu;  // 64-column KV units
   auto width_of = [&](int u) { return (u == nu - 1) ? p.last_w64 : 64; };
 
+  LOVR_TRACE(threadIdx.x == 0, 4000);
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQKV);
     mbar_init(k_full, 1);
@@ -134,8 +137,10 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
       const uint32_t idesc_o = make_idesc_16(128, 64, 0, 1, F16);  // B (=V) is MN-major
       uint32_t us[2] = {0, 0};  // fills issued per S buffer
       uint32_t up = 0;          // P units consumed
+      int trk = 0;
       auto issue_qk = [&](int u) {
         const int b = u & 1;
+        LOVR_TRACE(g == 0 && trk < 2, 2000 + (trk * 16 + u) * 6 + 0);
         mbar_wait(s_empty(g, b), (us[b] & 1) ^ 1);
         tc_fence_after();
         const uint32_t ka = smem_u32(sK + (u >> 1) * 16384) + (u & 1) * 8192;
@@ -145,10 +150,13 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
           umma_bf16_ss(tS[b], make_smem_desc_sw128(qa + k * 32, 16, 1024), make_smem_desc_sw128(ka + k * 32, 16, 1024),
                        idesc, k != 0);
         umma_commit(s_full(g, b));
+        LOVR_TRACE(g == 0 && trk < 2, 2000 + (trk * 16 + u) * 6 + 1);
         ++us[b];
       };
       auto issue_pv = [&](int u) {
+        LOVR_TRACE(g == 0 && trk < 2, 2000 + (trk * 16 + u) * 6 + 2);
         mbar_wait(p_full(g), up & 1);
+        LOVR_TRACE(g == 0 && trk < 2, 2000 + (trk * 16 + u) * 6 + 3);
         tc_fence_after();
         const uint32_t va = smem_u32(sV + (u >> 1) * 16384) + (u & 1) * 8192;
         const int steps = width_of(u) / 16;
@@ -156,9 +164,12 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
           umma_bf16_ss(tO, make_smem_desc_sw128(pa + s * 32, 16, 1024), make_smem_desc_sw128(va + s * 2048, 16384, 1024),
                        idesc_o, (u == 0 && s == 0) ? 0u : 1u);
         umma_commit(p_empty(g));
+        LOVR_TRACE(g == 0 && trk < 2, 2000 + (trk * 16 + u) * 6 + 4);
         ++up;
       };
+      LOVR_TRACE(g == 0, 4001);
       mbar_wait(k_full, 0);
+      LOVR_TRACE(g == 0, 4002);
       int k = 0;
       for (int t = g; t < q_tiles; t += 2, ++k) {
         mbar_wait(q_full(g), k & 1);
@@ -177,6 +188,7 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
           }
         }
         umma_commit(o_full(g));
+        ++trk;
       }
     }
   }
@@ -202,13 +214,17 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
         const int b = u & 1;
         const int w = width_of(u);
         const int valid = min(64, p.T - u * 64);
+        const bool tr = (g == 0 && warp == 4 && lane == 0 && k < 2);
+        LOVR_TRACE(tr, (k * 16 + u) * 8 + 0);
         mbar_wait(s_full(g, b), cs[b] & 1);
+        LOVR_TRACE(tr, (k * 16 + u) * 8 + 1);
         tc_fence_after();
         uint32_t buf[2][32];
         tmem_ld_32x32b_x32(tS[b], buf[0]);
         if (w == 64) tmem_ld_32x32b_x32(tS[b] + 32, buf[1]);
         tmem_ld_wait_dep(buf[0]);
         if (w == 64) tmem_ld_wait_dep(buf[1]);
+        LOVR_TRACE(tr, (k * 16 + u) * 8 + 2);
         // S unit is in registers: give the buffer back so the next-but-one QK^T can start
         tc_fence_before();
         __syncwarp();
@@ -293,7 +309,9 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
           }
         }
         // ---- hand the unit to the P·V issuer
+        LOVR_TRACE(tr, (k * 16 + u) * 8 + 3);
         mbar_wait(p_empty(g), (cp & 1) ^ 1);
+        LOVR_TRACE(tr, (k * 16 + u) * 8 + 4);
         const int nq = w >> 3;  // 16-byte chunks
 #pragma unroll
         for (int q = 0; q < 8; ++q)
@@ -301,10 +319,13 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full(g));
+        LOVR_TRACE(tr, (k * 16 + u) * 8 + 5);
         ++cp;
       }
       // ---------------- O / l -> global
+      LOVR_TRACE(g == 0 && warp == 4 && lane == 0 && k < 2, (k * 16 + 15) * 8 + 6);
       mbar_wait(o_full(g), k & 1);
+      LOVR_TRACE(g == 0 && warp == 4 && lane == 0 && k < 2, (k * 16 + 15) * 8 + 7);
       tc_fence_after();
       uint32_t o0[32], o1[32];
       tmem_ld_32x32b_x32(tO, o0);
@@ -333,6 +354,7 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
 
   tc_fence_before();
   __syncthreads();
+  LOVR_TRACE(threadIdx.x == 0, 4003);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);

@@ -300,6 +300,15 @@ int launch_attention(const void* qkv, void* out, int n_img, int T, int H, int im
   {
     const char* dbg = getenv("LOVR_ATTN_DEBUG");
     a.debug = dbg ? atoi(dbg) : 0;
+    a.trace = nullptr;
+    if (a.debug & 8) {
+      static long long* trace_buf = nullptr;
+      if (!trace_buf) cudaMalloc(&trace_buf, 8192 * sizeof(long long));
+      cudaMemsetAsync(trace_buf, 0, 8192 * sizeof(long long), s);
+      a.trace = trace_buf;
+      const char* path = getenv("LOVR_ATTN_TRACE_PTR");
+      if (path) { FILE* f = fopen(path, "w"); if (f) { fprintf(f, "%llu\n", (unsigned long long)trace_buf); fclose(f); } }
+    }
   }
   CUtensorMap tq;
   int rc;
