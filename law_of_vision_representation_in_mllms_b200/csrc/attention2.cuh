@@ -18,7 +18,7 @@
 //                 O += P_u·V_u (P from smem K-major, V as MN-major B operand: no transpose of V anywhere)
 //   warps 4-7     softmax of pipeline 0      warps 8-11   softmax of pipeline 1   (warp 3 idle)
 // Registers are rebalanced with setmaxnreg: the control warpgroup drops to 56, the softmax warpgroups rise to 224.
-// TMEM columns of pipeline g: [g*256 + 0, +64) S_a, [+64, +128) S_b, [+128, +192) O.
+// TMEM columns of pipeline g: [g*256 + 0, +64) S_a, [+64, +128) S_b, [+128, +192) O, [+192, +224) P (PT variant).
 #pragma once
 #include "attention.cuh"
 
@@ -31,7 +31,7 @@ inline size_t attn2_smem_bytes(int nb) { return static_cast<size_t>(2 * nb + 2 +
 
 #define LOVR_TRACE(cond, idx) do { if ((p.debug & 8) && blockIdx.x == 0 && (cond)) p.trace[(idx)] = clock64(); } while (0)
 
-template <bool F16>
+template <bool F16, bool PT>  // PT: P handed to the P·V MMA through TMEM (A operand from TMEM) instead of shared memory
 __global__ void __launch_bounds__(kAttn2Threads, 1)
 attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs p) {
   extern __shared__ uint8_t smem_raw[];
@@ -133,6 +133,7 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
       const int g = warp - 1;
       const uint32_t tS[2] = {tmem_base + g * 256, tmem_base + g * 256 + 64};
       const uint32_t tO = tmem_base + g * 256 + 128;
+      const uint32_t tP = tmem_base + g * 256 + 192;
       const uint32_t qa = smem_u32(sQ + g * 16384), pa = smem_u32(sP + g * 16384);
       const uint32_t idesc_o = make_idesc_16(128, 64, 0, 1, F16);  // B (=V) is MN-major
       uint32_t us[2] = {0, 0};  // fills issued per S buffer
@@ -160,9 +161,14 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
         tc_fence_after();
         const uint32_t va = smem_u32(sV + (u >> 1) * 16384) + (u & 1) * 8192;
         const int steps = width_of(u) / 16;
-        for (int s = 0; s < steps; ++s)
-          umma_bf16_ss(tO, make_smem_desc_sw128(pa + s * 32, 16, 1024), make_smem_desc_sw128(va + s * 2048, 16384, 1024),
-                       idesc_o, (u == 0 && s == 0) ? 0u : 1u);
+        for (int s = 0; s < steps; ++s) {
+          if constexpr (PT)  // A = P from TMEM: lane = row, 8 columns of packed 16-bit pairs per K=16 step
+            umma_bf16_ts(tO, tP + s * 8, make_smem_desc_sw128(va + s * 2048, 16384, 1024), idesc_o,
+                         (u == 0 && s == 0) ? 0u : 1u);
+          else
+            umma_bf16_ss(tO, make_smem_desc_sw128(pa + s * 32, 16, 1024), make_smem_desc_sw128(va + s * 2048, 16384, 1024),
+                         idesc_o, (u == 0 && s == 0) ? 0u : 1u);
+        }
         umma_commit(p_empty(g));
         LOVR_TRACE(g == 0 && trk < 2, 2000 + (trk * 16 + u) * 6 + 4);
         ++up;
@@ -201,6 +207,7 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
     const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
     const uint32_t tS[2] = {tmem_base + g * 256 + lane_sel, tmem_base + g * 256 + 64 + lane_sel};
     const uint32_t tO = tmem_base + g * 256 + 128 + lane_sel;
+    const uint32_t tPw = tmem_base + g * 256 + 192 + lane_sel;
     const uint32_t p_row = smem_u32(sP + g * 16384) + r * 128;
     const uint32_t row_sw = r & 7;
     const float c1 = p.scale * 1.4426950408889634f;
@@ -278,6 +285,8 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
         const float mc = m_used * c1;
         // ---- P = exp2(s*c1 - m*c1), row sum
         uint32_t pk[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) pk[i] = 0u;
         if (valid == 64) {
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
@@ -312,11 +321,17 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
         LOVR_TRACE(tr, (k * 16 + u) * 8 + 3);
         mbar_wait(p_empty(g), (cp & 1) ^ 1);
         LOVR_TRACE(tr, (k * 16 + u) * 8 + 4);
-        const int nq = w >> 3;  // 16-byte chunks
+        if constexpr (PT) {
+          tmem_st_32x32b_x32(tPw, pk);  // 64 P values of this row as 32 packed columns
+          tmem_st_wait();
+          tc_fence_before();
+        } else {
+          const int nq = w >> 3;  // 16-byte chunks
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          if (q < nq) st_shared_v4(p_row + ((q ^ row_sw) << 4), pk[q * 4 + 0], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
-        fence_proxy_async_smem();
+          for (int q = 0; q < 8; ++q)
+            if (q < nq) st_shared_v4(p_row + ((q ^ row_sw) << 4), pk[q * 4 + 0], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+          fence_proxy_async_smem();  // measured ~700 cycles per unit: the reason for the TMEM variant
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full(g));
         LOVR_TRACE(tr, (k * 16 + u) * 8 + 5);

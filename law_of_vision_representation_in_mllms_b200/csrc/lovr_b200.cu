@@ -313,18 +313,21 @@ int launch_attention(const void* qkv, void* out, int n_img, int T, int H, int im
   CUtensorMap tq;
   int rc;
   if ((rc = make_tmap(&tq, qkv, 2, 3 * D, T, n_img, 3 * D, static_cast<uint64_t>(3) * D * T, 64, 128))) return rc;
-  if (impl == LOVR_ATTN_TCGEN05_V2) {
+  if (impl == LOVR_ATTN_TCGEN05_V2 || impl == LOVR_ATTN_TCGEN05_V2_PTMEM) {
     const size_t smem2 = lovr::attn2_smem_bytes(nb);
     static size_t set_for2 = 0;
     if (smem2 > set_for2) {
-      CUDA_TRY(cudaFuncSetAttribute(lovr::attention2_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    static_cast<int>(smem2)));
-      CUDA_TRY(cudaFuncSetAttribute(lovr::attention2_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    static_cast<int>(smem2)));
+      CUDA_TRY(cudaFuncSetAttribute(lovr::attention2_tcgen05_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem2)));
+      CUDA_TRY(cudaFuncSetAttribute(lovr::attention2_tcgen05_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem2)));
+      CUDA_TRY(cudaFuncSetAttribute(lovr::attention2_tcgen05_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem2)));
+      CUDA_TRY(cudaFuncSetAttribute(lovr::attention2_tcgen05_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem2)));
       set_for2 = smem2;
     }
-    if (f16) lovr::attention2_tcgen05_kernel<true><<<n_img * H, lovr::kAttn2Threads, smem2, s>>>(tq, a);
-    else lovr::attention2_tcgen05_kernel<false><<<n_img * H, lovr::kAttn2Threads, smem2, s>>>(tq, a);
+    const bool pt = impl == LOVR_ATTN_TCGEN05_V2_PTMEM;
+    if (f16 && pt) lovr::attention2_tcgen05_kernel<true, true><<<n_img * H, lovr::kAttn2Threads, smem2, s>>>(tq, a);
+    else if (f16) lovr::attention2_tcgen05_kernel<true, false><<<n_img * H, lovr::kAttn2Threads, smem2, s>>>(tq, a);
+    else if (pt) lovr::attention2_tcgen05_kernel<false, true><<<n_img * H, lovr::kAttn2Threads, smem2, s>>>(tq, a);
+    else lovr::attention2_tcgen05_kernel<false, false><<<n_img * H, lovr::kAttn2Threads, smem2, s>>>(tq, a);
     LAUNCH_CHECK("attention2_tcgen05_kernel");
     return 0;
   }
