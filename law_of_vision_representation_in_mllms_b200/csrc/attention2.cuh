@@ -217,18 +217,21 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
     for (int t = g; t < q_tiles; t += 2, ++k) {
       float m_used = 0.f;  // row maximum (raw score units) the exponentials are currently taken against
       float l0 = 0.f, l1 = 0.f;
-      for (int u = 0; u < nu; ++u) {
+      // Software pipeline over units: the TMEM loads of unit u+1 are issued before the P hand-off of unit u, so their
+      // ~300-cycle latency and the s_full wake-up hide behind the tcgen05.st / mbarrier round trip of unit u.
+      uint32_t bufA[2][32], bufB[2][32];
+      {
+        mbar_wait(s_full(g, 0), cs[0] & 1);
+        tc_fence_after();
+        tmem_ld_32x32b_x32(tS[0], bufA[0]);
+        if (width_of(0) == 64) tmem_ld_32x32b_x32(tS[0] + 32, bufA[1]);
+      }
+      auto do_unit = [&](uint32_t (&buf)[2][32], uint32_t (&nxt)[2][32], const int u) {
         const int b = u & 1;
         const int w = width_of(u);
         const int valid = min(64, p.T - u * 64);
         const bool tr = (g == 0 && warp == 4 && lane == 0 && k < 2);
         LOVR_TRACE(tr, (k * 16 + u) * 8 + 0);
-        mbar_wait(s_full(g, b), cs[b] & 1);
-        LOVR_TRACE(tr, (k * 16 + u) * 8 + 1);
-        tc_fence_after();
-        uint32_t buf[2][32];
-        tmem_ld_32x32b_x32(tS[b], buf[0]);
-        if (w == 64) tmem_ld_32x32b_x32(tS[b] + 32, buf[1]);
         tmem_ld_wait_dep(buf[0]);
         if (w == 64) tmem_ld_wait_dep(buf[1]);
         LOVR_TRACE(tr, (k * 16 + u) * 8 + 2);
@@ -317,6 +320,15 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
             }
           }
         }
+        // ---- prefetch the next unit's scores (its QK^T was issued two units ago)
+        LOVR_TRACE(tr, (k * 16 + u) * 8 + 1);
+        if (u + 1 < nu) {
+          const int b2 = (u + 1) & 1;
+          mbar_wait(s_full(g, b2), cs[b2] & 1);
+          tc_fence_after();
+          tmem_ld_32x32b_x32(tS[b2], nxt[0]);
+          if (width_of(u + 1) == 64) tmem_ld_32x32b_x32(tS[b2] + 32, nxt[1]);
+        }
         // ---- hand the unit to the P·V issuer
         LOVR_TRACE(tr, (k * 16 + u) * 8 + 3);
         mbar_wait(p_empty(g), (cp & 1) ^ 1);
@@ -336,6 +348,10 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
         if (lane == 0) mbar_arrive(p_full(g));
         LOVR_TRACE(tr, (k * 16 + u) * 8 + 5);
         ++cp;
+      };
+      for (int u = 0; u < nu; u += 2) {
+        do_unit(bufA, bufB, u);
+        if (u + 1 < nu) do_unit(bufB, bufA, u + 1);
       }
       // ---------------- O / l -> global
       LOVR_TRACE(g == 0 && warp == 4 && lane == 0 && k < 2, (k * 16 + 15) * 8 + 6);

@@ -6,9 +6,9 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 import gpu_util as G
 n, T, H = 64, 577, 16
 qkv = torch.randn(n * T, 3 * H * 64, device="cuda").bfloat16()
-G.attention(qkv, n, T, H, 2); torch.cuda.synchronize()
+G.attention(qkv, n, T, H, 3); torch.cuda.synchronize()
 os.environ["LOVR_ATTN_DEBUG"] = "8"; os.environ["LOVR_ATTN_TRACE_PTR"] = "/tmp/trace_ptr.txt"
-G.attention(qkv, n, T, H, 2); torch.cuda.synchronize()
+G.attention(qkv, n, T, H, 3); torch.cuda.synchronize()
 ptr = int(open("/tmp/trace_ptr.txt").read())
 buf = (ctypes.c_longlong * 8192)()
 cudart = ctypes.CDLL("libcudart.so")
