@@ -129,60 +129,72 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
     }
   } else if (warp == 1 || warp == 2) {
     // ===================================================================== MMA issuer of pipeline g
-    if (lane == 0) {
+    // The whole warp walks the schedule and waits on the mbarriers (warp-uniform control flow, uniform registers);
+    // lane 0 issues tcgen05.mma / tcgen05.commit.  Descriptors are stepped with 32-bit adds.
+    {
       const int g = warp - 1;
       const uint32_t tS[2] = {tmem_base + g * 256, tmem_base + g * 256 + 64};
       const uint32_t tO = tmem_base + g * 256 + 128;
       const uint32_t tP = tmem_base + g * 256 + 192;
-      const uint32_t qa = smem_u32(sQ + g * 16384), pa = smem_u32(sP + g * 16384);
+      constexpr uint32_t kHi = smem_desc_hi_sw128(1024);
+      const uint32_t q_lo = smem_desc_lo(smem_u32(sQ + g * 16384), 16);
+      const uint32_t p_lo = smem_desc_lo(smem_u32(sP + g * 16384), 16);
+      const uint32_t k_lo0 = smem_desc_lo(smem_u32(sK), 16);
+      const uint32_t v_lo0 = smem_desc_lo(smem_u32(sV), 16384);
       const uint32_t idesc_o = make_idesc_16(128, 64, 0, 1, F16);  // B (=V) is MN-major
+      const uint32_t idesc_s64 = make_idesc_16(128, 64, 0, 0, F16);
+      const uint32_t idesc_slast = make_idesc_16(128, p.last_w64, 0, 0, F16);
       uint32_t us[2] = {0, 0};  // fills issued per S buffer
       uint32_t up = 0;          // P units consumed
       int trk = 0;
       auto issue_qk = [&](int u) {
         const int b = u & 1;
-        LOVR_TRACE(g == 0 && trk < 2, 2000 + (trk * 16 + u) * 6 + 0);
+        LOVR_TRACE(g == 0 && trk < 2 && lane == 0, 2000 + (trk * 16 + u) * 6 + 0);
         mbar_wait(s_empty(g, b), (us[b] & 1) ^ 1);
         tc_fence_after();
-        const uint32_t ka = smem_u32(sK + (u >> 1) * 16384) + (u & 1) * 8192;
-        const uint32_t idesc = make_idesc_16(128, width_of(u), 0, 0, F16);
+        if (lane == 0) {
+          const uint32_t k_lo = k_lo0 + u * (8192 >> 4);  // unit u = rows [64u, 64u+64) of the resident K
+          const uint32_t idesc = (u == nu - 1) ? idesc_slast : idesc_s64;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16_ss(tS[b], make_smem_desc_sw128(qa + k * 32, 16, 1024), make_smem_desc_sw128(ka + k * 32, 16, 1024),
-                       idesc, k != 0);
-        umma_commit(s_full(g, b));
-        LOVR_TRACE(g == 0 && trk < 2, 2000 + (trk * 16 + u) * 6 + 1);
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_ss(tS[b], smem_desc_join(kHi, q_lo + 2 * k), smem_desc_join(kHi, k_lo + 2 * k), idesc, k != 0);
+          umma_commit(s_full(g, b));
+        }
+        __syncwarp();
+        LOVR_TRACE(g == 0 && trk < 2 && lane == 0, 2000 + (trk * 16 + u) * 6 + 1);
         ++us[b];
       };
       auto issue_pv = [&](int u) {
-        LOVR_TRACE(g == 0 && trk < 2, 2000 + (trk * 16 + u) * 6 + 2);
+        LOVR_TRACE(g == 0 && trk < 2 && lane == 0, 2000 + (trk * 16 + u) * 6 + 2);
         mbar_wait(p_full(g), up & 1);
-        LOVR_TRACE(g == 0 && trk < 2, 2000 + (trk * 16 + u) * 6 + 3);
+        LOVR_TRACE(g == 0 && trk < 2 && lane == 0, 2000 + (trk * 16 + u) * 6 + 3);
         tc_fence_after();
-        const uint32_t va = smem_u32(sV + (u >> 1) * 16384) + (u & 1) * 8192;
-        const int steps = width_of(u) / 16;
-        for (int s = 0; s < steps; ++s) {
-          if constexpr (PT)  // A = P from TMEM: lane = row, 8 columns of packed 16-bit pairs per K=16 step
-            umma_bf16_ts(tO, tP + s * 8, make_smem_desc_sw128(va + s * 2048, 16384, 1024), idesc_o,
-                         (u == 0 && s == 0) ? 0u : 1u);
-          else
-            umma_bf16_ss(tO, make_smem_desc_sw128(pa + s * 32, 16, 1024), make_smem_desc_sw128(va + s * 2048, 16384, 1024),
-                         idesc_o, (u == 0 && s == 0) ? 0u : 1u);
+        if (lane == 0) {
+          const uint32_t v_lo = v_lo0 + u * (8192 >> 4);
+          const int steps = width_of(u) / 16;
+          for (int s = 0; s < steps; ++s) {
+            const uint64_t vdesc = smem_desc_join(kHi, v_lo + s * (2048 >> 4));
+            if constexpr (PT)  // A = P from TMEM: lane = row, 8 columns of packed 16-bit pairs per K=16 step
+              umma_bf16_ts(tO, tP + s * 8, vdesc, idesc_o, (u == 0 && s == 0) ? 0u : 1u);
+            else
+              umma_bf16_ss(tO, smem_desc_join(kHi, p_lo + 2 * s), vdesc, idesc_o, (u == 0 && s == 0) ? 0u : 1u);
+          }
+          umma_commit(p_empty(g));
         }
-        umma_commit(p_empty(g));
-        LOVR_TRACE(g == 0 && trk < 2, 2000 + (trk * 16 + u) * 6 + 4);
+        __syncwarp();
+        LOVR_TRACE(g == 0 && trk < 2 && lane == 0, 2000 + (trk * 16 + u) * 6 + 4);
         ++up;
       };
-      LOVR_TRACE(g == 0, 4001);
+      LOVR_TRACE(g == 0 && lane == 0, 4001);
       mbar_wait(k_full, 0);
-      LOVR_TRACE(g == 0, 4002);
+      LOVR_TRACE(g == 0 && lane == 0, 4002);
       int k = 0;
       for (int t = g; t < q_tiles; t += 2, ++k) {
         mbar_wait(q_full(g), k & 1);
         int issued = 0;
         issue_qk(issued++);
         if (nu > 1) issue_qk(issued++);
-        if (issued == nu) umma_commit(q_empty(g));
+        if (issued == nu && lane == 0) umma_commit(q_empty(g));
         if (k == 0) mbar_wait(v_full, 0);
         mbar_wait(o_empty(g), (k & 1) ^ 1);  // epilogue of this pipeline's previous tile has read O
         tc_fence_after();
@@ -190,10 +202,11 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
           issue_pv(u);
           if (issued < nu) {
             issue_qk(issued++);
-            if (issued == nu) umma_commit(q_empty(g));  // every QK^T of this tile issued: Q reusable when they retire
+            if (issued == nu && lane == 0) umma_commit(q_empty(g));  // every QK^T of this tile issued
           }
         }
-        umma_commit(o_full(g));
+        if (lane == 0) umma_commit(o_full(g));
+        __syncwarp();
         ++trk;
       }
     }
@@ -217,21 +230,18 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
     for (int t = g; t < q_tiles; t += 2, ++k) {
       float m_used = 0.f;  // row maximum (raw score units) the exponentials are currently taken against
       float l0 = 0.f, l1 = 0.f;
-      // Software pipeline over units: the TMEM loads of unit u+1 are issued before the P hand-off of unit u, so their
-      // ~300-cycle latency and the s_full wake-up hide behind the tcgen05.st / mbarrier round trip of unit u.
-      uint32_t bufA[2][32], bufB[2][32];
-      {
-        mbar_wait(s_full(g, 0), cs[0] & 1);
-        tc_fence_after();
-        tmem_ld_32x32b_x32(tS[0], bufA[0]);
-        if (width_of(0) == 64) tmem_ld_32x32b_x32(tS[0] + 32, bufA[1]);
-      }
-      auto do_unit = [&](uint32_t (&buf)[2][32], uint32_t (&nxt)[2][32], const int u) {
+      for (int u = 0; u < nu; ++u) {
         const int b = u & 1;
         const int w = width_of(u);
         const int valid = min(64, p.T - u * 64);
         const bool tr = (g == 0 && warp == 4 && lane == 0 && k < 2);
         LOVR_TRACE(tr, (k * 16 + u) * 8 + 0);
+        mbar_wait(s_full(g, b), cs[b] & 1);
+        LOVR_TRACE(tr, (k * 16 + u) * 8 + 1);
+        tc_fence_after();
+        uint32_t buf[2][32];
+        tmem_ld_32x32b_x32(tS[b], buf[0]);
+        if (w == 64) tmem_ld_32x32b_x32(tS[b] + 32, buf[1]);
         tmem_ld_wait_dep(buf[0]);
         if (w == 64) tmem_ld_wait_dep(buf[1]);
         LOVR_TRACE(tr, (k * 16 + u) * 8 + 2);
@@ -320,15 +330,6 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
             }
           }
         }
-        // ---- prefetch the next unit's scores (its QK^T was issued two units ago)
-        LOVR_TRACE(tr, (k * 16 + u) * 8 + 1);
-        if (u + 1 < nu) {
-          const int b2 = (u + 1) & 1;
-          mbar_wait(s_full(g, b2), cs[b2] & 1);
-          tc_fence_after();
-          tmem_ld_32x32b_x32(tS[b2], nxt[0]);
-          if (width_of(u + 1) == 64) tmem_ld_32x32b_x32(tS[b2] + 32, nxt[1]);
-        }
         // ---- hand the unit to the P·V issuer
         LOVR_TRACE(tr, (k * 16 + u) * 8 + 3);
         mbar_wait(p_empty(g), (cp & 1) ^ 1);
@@ -348,10 +349,6 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
         if (lane == 0) mbar_arrive(p_full(g));
         LOVR_TRACE(tr, (k * 16 + u) * 8 + 5);
         ++cp;
-      };
-      for (int u = 0; u < nu; u += 2) {
-        do_unit(bufA, bufB, u);
-        if (u + 1 < nu) do_unit(bufB, bufA, u + 1);
       }
       // ---------------- O / l -> global
       LOVR_TRACE(g == 0 && warp == 4 && lane == 0 && k < 2, (k * 16 + 15) * 8 + 6);

@@ -150,34 +150,40 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
-        for (int ni = 0; ni < p.n_inner; ++ni) {
-          mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+    // The whole warp walks the (warp-uniform) schedule and waits on the mbarriers; lane 0 alone issues tcgen05.mma
+    // and tcgen05.commit.  Descriptors are stepped with one 32-bit add: a single divergent thread rebuilding 64-bit
+    // descriptors per MMA cost ~150 issue cycles per instruction (measured), i.e. more than the 128 cycles the MMA
+    // itself occupies the tensor pipe.
+    constexpr uint32_t kDescHi = smem_desc_hi_sw128(1024);
+    const uint32_t a_lo0 = smem_desc_lo(smem_u32(stage_base), 16);
+    const uint32_t b_lo0 = smem_desc_lo(smem_u32(stage_base) + L::kABytes, 16);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+      for (int ni = 0; ni < p.n_inner; ++ni) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + acc * BN;
-          for (int kb = 0; kb < k_blocks; ++kb) {
-            mbar_wait(&full_bar[stage], phase);
-            tc_fence_after();
-            const uint32_t sa = smem_u32(stage_base + stage * L::kStageBytes);
-            const uint32_t sb = sa + L::kABytes;
+          if (lane == 0) {
+            const uint32_t a_lo = a_lo0 + stage * (L::kStageBytes >> 4);
+            const uint32_t b_lo = b_lo0 + stage * (L::kStageBytes >> 4);
 #pragma unroll
-            for (int k = 0; k < kBK / 16; ++k) {
-              const uint64_t adesc = make_smem_desc_sw128(sa + k * 32, 16, 1024);
-              const uint64_t bdesc = make_smem_desc_sw128(sb + k * 32, 16, 1024);
-              umma_bf16_ss(d_tmem, adesc, bdesc, kIdesc, (kb | k) != 0 ? 1u : 0u);
-            }
+            for (int k = 0; k < kBK / 16; ++k)
+              umma_bf16_ss(d_tmem, smem_desc_join(kDescHi, a_lo + 2 * k), smem_desc_join(kDescHi, b_lo + 2 * k), kIdesc,
+                           (kb | k) != 0 ? 1u : 0u);
             umma_commit(&empty_bar[stage]);  // smem stage reusable once these MMAs retire
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
+            if (kb == k_blocks - 1) umma_commit(&tmem_full[acc]);
           }
-          umma_commit(&tmem_full[acc]);
-          acc ^= 1;
-          if (acc == 0) acc_phase ^= 1;
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
       }
     }
   } else {

@@ -218,6 +218,17 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uin
   d |= 2ull << 61;
   return d;
 }
+// Cheap form for the issue loop: the high word is constant per layout; the low word is (addr >> 4) | (LBO >> 4) << 16,
+// so stepping along K or to another pipeline stage is one 32-bit add on the low word.
+__device__ __forceinline__ constexpr uint32_t smem_desc_hi_sw128(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);
+}
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr >> 4) & 0x3FFF) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+}
+__device__ __forceinline__ uint64_t smem_desc_join(uint32_t hi, uint32_t lo) {
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32:
 //   [4,6) c_format=1 (F32)  [7,10) a_format=1 (BF16)  [10,13) b_format=1 (BF16)
 //   [15] a_major (0=K,1=MN) [16] b_major  [17,23) N>>3  [24,29) M>>4
