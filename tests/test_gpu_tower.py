@@ -39,7 +39,7 @@ def tolerance_for(name, rec):
     return 0.75 * ref if ref is not None else 1.2e-2
 
 
-def _build(case, attn_impl=_lib.ATTN_TCGEN05, operand_dtype="bf16"):
+def _build(case, attn_impl=_lib.ATTN_TCGEN05_V2_PTMEM, operand_dtype="bf16"):
     name, key, nl, size, n, sl, sf = case
     spec, sd, imgs = vit_case_inputs(case)
     args = types.SimpleNamespace(mm_vision_select_layer=sl, mm_vision_select_feature=sf, lovr_spec=spec,
@@ -91,11 +91,12 @@ def test_tower_matches_oracle_full_tensor_and_simt_attention(cname):
     want = vit_oracle.tower_forward(cw, spec.at_resolution(size), imgs, sl, tower.select_feature)
     out = tower(imgs.cuda()).cpu()
     e1 = G.rel_err(out, want)
-    tower._attn_impl = _lib.ATTN_SIMT_CHECK
-    out2 = tower(imgs.cuda()).cpu()
-    e2 = G.rel_err(out2, want)
-    print(f"{cname}: tcgen05 attention {e1:.3e}, simt attention {e2:.3e}")
-    assert e1 < 9e-3 and e2 < 9e-3          # stress weights, 2 layers run (see module docstring)
+    errs = {}
+    for name_, impl in (("simt", _lib.ATTN_SIMT_CHECK), ("tcgen05_v1", _lib.ATTN_TCGEN05), ("tcgen05_v2_smemP", _lib.ATTN_TCGEN05_V2)):
+        tower._attn_impl = impl
+        errs[name_] = G.rel_err(tower(imgs.cuda()).cpu(), want)
+    print(f"{cname}: default attention {e1:.3e}, others {errs}")
+    assert e1 < 9e-3 and max(errs.values()) < 9e-3          # stress weights, 2 layers run (see module docstring)
 
 
 def test_caller_dtype_list_input_and_batch_chunking():
