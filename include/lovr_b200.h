@@ -30,9 +30,10 @@ enum { LOVR_DT_F32 = 0, LOVR_DT_BF16 = 1, LOVR_DT_F16 = 2 };
 /* hidden_act of the HF config: quick_gelu (openai CLIP), gelu (OpenCLIP, DINOv2), gelu_pytorch_tanh (SigLIP) */
 enum { LOVR_ACT_NONE = 0, LOVR_ACT_QUICK_GELU = 1, LOVR_ACT_GELU_ERF = 2, LOVR_ACT_GELU_TANH = 3 };
 enum { LOVR_EPI_BF16 = 0, LOVR_EPI_RESID_F32 = 1, LOVR_EPI_F32 = 2 };
-/* attention implementations: 0 = tcgen05, one softmax pipeline per CTA; 2 = tcgen05, single-pass online softmax, two pipelines per CTA, P via shared memory; 3 = same with P via TMEM;
+/* attention implementations: 0 = tcgen05, one softmax pipeline per CTA; 2 = tcgen05, single-pass online softmax, two pipelines per CTA, P via shared memory; 3 = same with P via TMEM; 4 = three pipelines, P via TMEM;
  * 1 = CUDA-core cross-check used only by tests */
-enum { LOVR_ATTN_TCGEN05 = 0, LOVR_ATTN_SIMT_CHECK = 1, LOVR_ATTN_TCGEN05_V2 = 2, LOVR_ATTN_TCGEN05_V2_PTMEM = 3 };
+enum { LOVR_ATTN_TCGEN05 = 0, LOVR_ATTN_SIMT_CHECK = 1, LOVR_ATTN_TCGEN05_V2 = 2, LOVR_ATTN_TCGEN05_V2_PTMEM = 3,
+       LOVR_ATTN_TCGEN05_V2_3PIPE = 4 };
 
 int lovr_abi_version(void);
 const char* lovr_last_error(void);

@@ -24,24 +24,33 @@
 
 namespace lovr {
 
-constexpr int kAttn2Threads = 12 * 32;  // warpgroup 0: TMA + 2 MMA issuers (+1 idle warp); warpgroups 1,2: softmax
+// NP = number of softmax pipelines per CTA (query tile t -> pipeline t % NP).  NP = 2: S double-buffered per pipeline.
+// NP = 3: S single-buffered, P through TMEM only; with 5 query tiles (T = 577) the per-CTA critical path is 2 tile times
+// instead of 3, and a third softmax warp per SM sub-partition fills more issue slots.
+constexpr int attn2_threads(int np) { return (4 + 4 * np) * 32; }  // warpgroup 0: TMA + MMA issuers; then NP softmax warpgroups
 constexpr float kAttnRescaleLog2 = 8.0f;
 
-inline size_t attn2_smem_bytes(int nb) { return static_cast<size_t>(2 * nb + 2 + 2) * 16384 + 512 + 1024; }
+inline size_t attn2_smem_bytes(int nb, int np, bool pt) {
+  return static_cast<size_t>(2 * nb + np + (pt ? 0 : np)) * 16384 + 512 + 1024;
+}
 
 #define LOVR_TRACE(cond, idx) do { if ((p.debug & 8) && blockIdx.x == 0 && (cond)) p.trace[(idx)] = clock64(); } while (0)
 
-template <bool F16, bool PT>  // PT: P handed to the P·V MMA through TMEM (A operand from TMEM) instead of shared memory
-__global__ void __launch_bounds__(kAttn2Threads, 1)
+template <bool F16, bool PT, int NP>  // PT: P handed to the P·V MMA through TMEM (A operand from TMEM) instead of smem
+__global__ void __launch_bounds__(attn2_threads(NP), 1)
 attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int nb = p.nb;
   uint8_t* sK = smem;
   uint8_t* sV = sK + nb * 16384;
-  uint8_t* sQ = sV + nb * 16384;  // [2 pipelines] x 16 KB
-  uint8_t* sP = sQ + 2 * 16384;   // [2 pipelines] x 16 KB (one K-major atom: 128 rows x 64 columns)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * 16384);
+  static_assert(NP == 2 || (NP == 3 && PT), "3 pipelines need P in TMEM (shared memory is full)");
+  constexpr int NBUF = (NP == 2) ? 2 : 1;            // S buffers per pipeline
+  constexpr int kPipeCols = (NP == 2) ? 256 : 160;   // TMEM columns per pipeline
+  constexpr int kOCol = NBUF * 64, kPCol = NBUF * 64 + 64;
+  uint8_t* sQ = sV + nb * 16384;  // [NP pipelines] x 16 KB
+  uint8_t* sP = sQ + NP * 16384;  // [NP pipelines] x 16 KB (one K-major atom: 128 rows x 64 columns), unused when PT
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + (PT ? 0 : NP) * 16384);
   uint64_t* k_full = bars + 0;
   uint64_t* v_full = bars + 1;
   auto q_full = [&](int g) { return bars + 2 + 10 * g + 0; };
@@ -52,7 +61,7 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
   auto p_empty = [&](int g) { return bars + 2 + 10 * g + 7; };
   auto o_full = [&](int g) { return bars + 2 + 10 * g + 8; };
   auto o_empty = [&](int g) { return bars + 2 + 10 * g + 9; };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 + 10 * NP);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.x / p.H, h = blockIdx.x % p.H;
@@ -66,7 +75,7 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
     tma_prefetch_desc(&tmQKV);
     mbar_init(k_full, 1);
     mbar_init(v_full, 1);
-    for (int g = 0; g < 2; ++g) {
+    for (int g = 0; g < NP; ++g) {
       mbar_init(q_full(g), 1);
       mbar_init(q_empty(g), 1);
       for (int b = 0; b < 2; ++b) {
@@ -90,14 +99,14 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 4) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(NP == 2 ? 56 : 40));
   if (warp == 0) {
     // ===================================================================== TMA
     if (lane == 0) {
       mbar_arrive_expect_tx(k_full, nb * 16384);
       for (int j = 0; j < nb; ++j) tma_load_3d(sK + j * 16384, &tmQKV, k_full, D + h * 64, j * 128, n);
-      int next_k[2] = {0, 0};  // per pipeline: index of its next tile (tile = 2*k + g)
-      for (int g = 0; g < 2; ++g) {
+      int next_k[NP] = {};  // per pipeline: index of its next tile (tile = NP*k + g)
+      for (int g = 0; g < NP; ++g) {
         if (g < q_tiles) {
           mbar_arrive_expect_tx(q_full(g), 16384);
           tma_load_3d(sQ + g * 16384, &tmQKV, q_full(g), h * 64, g * 128, n);
@@ -110,8 +119,8 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
       const long long t0 = clock64();
       for (;;) {
         bool pending = false;
-        for (int g = 0; g < 2; ++g) {
-          const int t = 2 * next_k[g] + g;
+        for (int g = 0; g < NP; ++g) {
+          const int t = NP * next_k[g] + g;
           if (t >= q_tiles) continue;
           pending = true;
           if (mbar_try_wait(q_empty(g), (next_k[g] - 1) & 1)) {  // previous tile's QK^T all retired
@@ -127,18 +136,18 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
         }
       }
     }
-  } else if (warp == 1 || warp == 2) {
+  } else if (warp >= 1 && warp <= NP) {
     // ===================================================================== MMA issuer of pipeline g
     // The whole warp walks the schedule and waits on the mbarriers (warp-uniform control flow, uniform registers);
     // lane 0 issues tcgen05.mma / tcgen05.commit.  Descriptors are stepped with 32-bit adds.
     {
       const int g = warp - 1;
-      const uint32_t tS[2] = {tmem_base + g * 256, tmem_base + g * 256 + 64};
-      const uint32_t tO = tmem_base + g * 256 + 128;
-      const uint32_t tP = tmem_base + g * 256 + 192;
+      const uint32_t tS[2] = {tmem_base + g * kPipeCols, tmem_base + g * kPipeCols + (NBUF - 1) * 64};
+      const uint32_t tO = tmem_base + g * kPipeCols + kOCol;
+      const uint32_t tP = tmem_base + g * kPipeCols + kPCol;
       constexpr uint32_t kHi = smem_desc_hi_sw128(1024);
       const uint32_t q_lo = smem_desc_lo(smem_u32(sQ + g * 16384), 16);
-      const uint32_t p_lo = smem_desc_lo(smem_u32(sP + g * 16384), 16);
+      const uint32_t p_lo = smem_desc_lo(smem_u32(sP + (PT ? 0 : g) * 16384), 16);
       const uint32_t k_lo0 = smem_desc_lo(smem_u32(sK), 16);
       const uint32_t v_lo0 = smem_desc_lo(smem_u32(sV), 16384);
       const uint32_t idesc_o = make_idesc_16(128, 64, 0, 1, F16);  // B (=V) is MN-major
@@ -148,7 +157,7 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
       uint32_t up = 0;          // P units consumed
       int trk = 0;
       auto issue_qk = [&](int u) {
-        const int b = u & 1;
+        const int b = u & (NBUF - 1);
         LOVR_TRACE(g == 0 && trk < 2 && lane == 0, 2000 + (trk * 16 + u) * 6 + 0);
         mbar_wait(s_empty(g, b), (us[b] & 1) ^ 1);
         tc_fence_after();
@@ -189,18 +198,24 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
       mbar_wait(k_full, 0);
       LOVR_TRACE(g == 0 && lane == 0, 4002);
       int k = 0;
-      for (int t = g; t < q_tiles; t += 2, ++k) {
+      for (int t = g; t < q_tiles; t += NP, ++k) {
         mbar_wait(q_full(g), k & 1);
         int issued = 0;
         issue_qk(issued++);
-        if (nu > 1) issue_qk(issued++);
+        if (NBUF == 2 && nu > 1) issue_qk(issued++);
         if (issued == nu && lane == 0) umma_commit(q_empty(g));
         if (k == 0) mbar_wait(v_full, 0);
         mbar_wait(o_empty(g), (k & 1) ^ 1);  // epilogue of this pipeline's previous tile has read O
         tc_fence_after();
         for (int u = 0; u < nu; ++u) {
+          // single S buffer: S(u) is already in the softmax warps' registers, so QK^T(u+1) goes first and runs while
+          // they exponentiate; double buffer: QK^T(u+2) follows P·V(u)
+          if (NBUF == 1 && issued < nu) {
+            issue_qk(issued++);
+            if (issued == nu && lane == 0) umma_commit(q_empty(g));
+          }
           issue_pv(u);
-          if (issued < nu) {
+          if (NBUF == 2 && issued < nu) {
             issue_qk(issued++);
             if (issued == nu && lane == 0) umma_commit(q_empty(g));  // every QK^T of this tile issued
           }
@@ -213,25 +228,25 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
   }
   } else {
     // ===================================================================== softmax pipelines
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(NP == 2 ? 224 : 152));
     const int g = (warp - 4) >> 2;
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
     const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t tS[2] = {tmem_base + g * 256 + lane_sel, tmem_base + g * 256 + 64 + lane_sel};
-    const uint32_t tO = tmem_base + g * 256 + 128 + lane_sel;
-    const uint32_t tPw = tmem_base + g * 256 + 192 + lane_sel;
-    const uint32_t p_row = smem_u32(sP + g * 16384) + r * 128;
+    const uint32_t tS[2] = {tmem_base + g * kPipeCols + lane_sel, tmem_base + g * kPipeCols + (NBUF - 1) * 64 + lane_sel};
+    const uint32_t tO = tmem_base + g * kPipeCols + kOCol + lane_sel;
+    const uint32_t tPw = tmem_base + g * kPipeCols + kPCol + lane_sel;
+    const uint32_t p_row = smem_u32(sP + (PT ? 0 : g) * 16384) + r * 128;
     const uint32_t row_sw = r & 7;
     const float c1 = p.scale * 1.4426950408889634f;
     uint32_t cs[2] = {0, 0};  // S fills consumed per buffer
     uint32_t cp = 0;          // P units produced
     int k = 0;
-    for (int t = g; t < q_tiles; t += 2, ++k) {
+    for (int t = g; t < q_tiles; t += NP, ++k) {
       float m_used = 0.f;  // row maximum (raw score units) the exponentials are currently taken against
       float l0 = 0.f, l1 = 0.f;
       for (int u = 0; u < nu; ++u) {
-        const int b = u & 1;
+        const int b = u & (NBUF - 1);
         const int w = width_of(u);
         const int valid = min(64, p.T - u * 64);
         const bool tr = (g == 0 && warp == 4 && lane == 0 && k < 2);

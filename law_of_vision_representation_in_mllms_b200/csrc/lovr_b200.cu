@@ -313,21 +313,25 @@ int launch_attention(const void* qkv, void* out, int n_img, int T, int H, int im
   CUtensorMap tq;
   int rc;
   if ((rc = make_tmap(&tq, qkv, 2, 3 * D, T, n_img, 3 * D, static_cast<uint64_t>(3) * D * T, 64, 128))) return rc;
-  if (impl == LOVR_ATTN_TCGEN05_V2 || impl == LOVR_ATTN_TCGEN05_V2_PTMEM) {
-    const size_t smem2 = lovr::attn2_smem_bytes(nb);
-    static size_t set_for2 = 0;
-    if (smem2 > set_for2) {
-      CUDA_TRY(cudaFuncSetAttribute(lovr::attention2_tcgen05_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem2)));
-      CUDA_TRY(cudaFuncSetAttribute(lovr::attention2_tcgen05_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem2)));
-      CUDA_TRY(cudaFuncSetAttribute(lovr::attention2_tcgen05_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem2)));
-      CUDA_TRY(cudaFuncSetAttribute(lovr::attention2_tcgen05_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem2)));
-      set_for2 = smem2;
-    }
-    const bool pt = impl == LOVR_ATTN_TCGEN05_V2_PTMEM;
-    if (f16 && pt) lovr::attention2_tcgen05_kernel<true, true><<<n_img * H, lovr::kAttn2Threads, smem2, s>>>(tq, a);
-    else if (f16) lovr::attention2_tcgen05_kernel<true, false><<<n_img * H, lovr::kAttn2Threads, smem2, s>>>(tq, a);
-    else if (pt) lovr::attention2_tcgen05_kernel<false, true><<<n_img * H, lovr::kAttn2Threads, smem2, s>>>(tq, a);
-    else lovr::attention2_tcgen05_kernel<false, false><<<n_img * H, lovr::kAttn2Threads, smem2, s>>>(tq, a);
+  if (impl == LOVR_ATTN_TCGEN05_V2 || impl == LOVR_ATTN_TCGEN05_V2_PTMEM || impl == LOVR_ATTN_TCGEN05_V2_3PIPE) {
+    const int np = impl == LOVR_ATTN_TCGEN05_V2_3PIPE ? 3 : 2;
+    const bool pt = impl != LOVR_ATTN_TCGEN05_V2;
+    const size_t smem2 = lovr::attn2_smem_bytes(nb, np, pt);
+    const int threads = lovr::attn2_threads(np);
+#define LOVR_ATTN2_LAUNCH(F16_, PT_, NP_)                                                                             \
+  do {                                                                                                               \
+    auto kern = lovr::attention2_tcgen05_kernel<F16_, PT_, NP_>;                                                     \
+    static size_t set_for2 = 0;                                                                                      \
+    if (smem2 > set_for2) {                                                                                          \
+      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem2)));    \
+      set_for2 = smem2;                                                                                              \
+    }                                                                                                                \
+    kern<<<n_img * H, threads, smem2, s>>>(tq, a);                                                                   \
+  } while (0)
+    if (np == 3) { if (f16) LOVR_ATTN2_LAUNCH(true, true, 3); else LOVR_ATTN2_LAUNCH(false, true, 3); }
+    else if (pt) { if (f16) LOVR_ATTN2_LAUNCH(true, true, 2); else LOVR_ATTN2_LAUNCH(false, true, 2); }
+    else { if (f16) LOVR_ATTN2_LAUNCH(true, false, 2); else LOVR_ATTN2_LAUNCH(false, false, 2); }
+#undef LOVR_ATTN2_LAUNCH
     LAUNCH_CHECK("attention2_tcgen05_kernel");
     return 0;
   }

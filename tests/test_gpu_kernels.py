@@ -82,7 +82,8 @@ def test_attention_fp16_operands():
     n, T, H = 2, 577, 16
     qkv = _rand((n * T, 3 * H * 64), 31, 1.0, torch.float16)
     want = _torch_attention(qkv, n, T, H)
-    for impl in (_lib.ATTN_TCGEN05, _lib.ATTN_TCGEN05_V2, _lib.ATTN_TCGEN05_V2_PTMEM, _lib.ATTN_SIMT_CHECK):
+    for impl in (_lib.ATTN_TCGEN05, _lib.ATTN_TCGEN05_V2, _lib.ATTN_TCGEN05_V2_PTMEM, _lib.ATTN_TCGEN05_V2_3PIPE,
+                 _lib.ATTN_SIMT_CHECK):
         got = G.attention(qkv, n, T, H, impl)
         assert got.dtype == torch.float16
         assert G.rel_err(got, want) < 6e-4
@@ -121,7 +122,8 @@ def _torch_attention(qkv, n, T, H):
     return (p @ v).transpose(1, 2).reshape(n * T, D)
 
 
-@pytest.mark.parametrize("impl", [_lib.ATTN_SIMT_CHECK, _lib.ATTN_TCGEN05, _lib.ATTN_TCGEN05_V2, _lib.ATTN_TCGEN05_V2_PTMEM])
+@pytest.mark.parametrize("impl", [_lib.ATTN_SIMT_CHECK, _lib.ATTN_TCGEN05, _lib.ATTN_TCGEN05_V2, _lib.ATTN_TCGEN05_V2_PTMEM,
+                                  _lib.ATTN_TCGEN05_V2_3PIPE])
 @pytest.mark.parametrize("n,T,H,scale", [(2, 577, 16, 1.0), (3, 257, 16, 2.0), (2, 196, 12, 1.0), (1, 50, 16, 1.0),
                                           (1, 128, 16, 3.0), (1, 640, 16, 1.0)])
 def test_attention(impl, n, T, H, scale):
