@@ -13,6 +13,7 @@ OK, E_ARG, E_CUDA, E_UNSUPPORTED, E_NOMEM = 0, -1, -2, -3, -4
 DT_F32, DT_BF16, DT_F16 = 0, 1, 2
 EPI_BF16, EPI_RESID_F32, EPI_F32 = 0, 1, 2
 ATTN_TCGEN05, ATTN_SIMT_CHECK, ATTN_TCGEN05_V2, ATTN_TCGEN05_V2_PTMEM, ATTN_TCGEN05_V2_3PIPE = 0, 1, 2, 3, 4
+ATTN_AUTO = 5
 
 # every symbol include/lovr_b200.h declares (tests/test_abi.py checks the library exports all of them)
 EXPORTS = [

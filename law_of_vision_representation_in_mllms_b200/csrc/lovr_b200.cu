@@ -313,6 +313,7 @@ int launch_attention(const void* qkv, void* out, int n_img, int T, int H, int im
   CUtensorMap tq;
   int rc;
   if ((rc = make_tmap(&tq, qkv, 2, 3 * D, T, n_img, 3 * D, static_cast<uint64_t>(3) * D * T, 64, 128))) return rc;
+  if (impl == LOVR_ATTN_AUTO) impl = (T > 256) ? LOVR_ATTN_TCGEN05_V2_3PIPE : LOVR_ATTN_TCGEN05_V2_PTMEM;  // >= 3 query tiles
   if (impl == LOVR_ATTN_TCGEN05_V2 || impl == LOVR_ATTN_TCGEN05_V2_PTMEM || impl == LOVR_ATTN_TCGEN05_V2_3PIPE) {
     const int np = impl == LOVR_ATTN_TCGEN05_V2_3PIPE ? 3 : 2;
     const bool pt = impl != LOVR_ATTN_TCGEN05_V2;

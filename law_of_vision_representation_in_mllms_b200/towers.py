@@ -88,7 +88,7 @@ class _NativeTower:
             _lib.lib().lovr_tower_destroy(h)
             self.handle = C.c_void_p()
 
-    def forward_into(self, pixels, out, n_run, drop_cls, col_off=0, attn_impl=_lib.ATTN_TCGEN05_V2_PTMEM):
+    def forward_into(self, pixels, out, n_run, drop_cls, col_off=0, attn_impl=_lib.ATTN_AUTO):
         """pixels [n,3,R,R] on device; out [n,P,Dtot] on device; writes out[:, :, col_off:col_off+D]."""
         L = _lib.lib()
         n = pixels.shape[0]
@@ -120,7 +120,7 @@ class _B200VisionTower(nn.Module):
         self._native = {}          # image_size -> _NativeTower
         self._state_dict = None
         self.image_processor = None
-        self._attn_impl = _lib.ATTN_TCGEN05_V2_PTMEM   # single-pass online softmax, two pipelines, P through TMEM
+        self._attn_impl = _lib.ATTN_AUTO   # single-pass online softmax, P through TMEM, 3 or 2 pipelines by token count
         if not delay_load:
             self.load_model()
 

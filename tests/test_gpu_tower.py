@@ -39,7 +39,7 @@ def tolerance_for(name, rec):
     return 0.75 * ref if ref is not None else 1.2e-2
 
 
-def _build(case, attn_impl=_lib.ATTN_TCGEN05_V2_PTMEM, operand_dtype="bf16"):
+def _build(case, attn_impl=_lib.ATTN_AUTO, operand_dtype="bf16"):
     name, key, nl, size, n, sl, sf = case
     spec, sd, imgs = vit_case_inputs(case)
     args = types.SimpleNamespace(mm_vision_select_layer=sl, mm_vision_select_feature=sf, lovr_spec=spec,
@@ -92,7 +92,8 @@ def test_tower_matches_oracle_full_tensor_and_simt_attention(cname):
     out = tower(imgs.cuda()).cpu()
     e1 = G.rel_err(out, want)
     errs = {}
-    for name_, impl in (("simt", _lib.ATTN_SIMT_CHECK), ("tcgen05_v1", _lib.ATTN_TCGEN05), ("tcgen05_v2_smemP", _lib.ATTN_TCGEN05_V2)):
+    for name_, impl in (("simt", _lib.ATTN_SIMT_CHECK), ("tcgen05_v1", _lib.ATTN_TCGEN05), ("tcgen05_v2_smemP", _lib.ATTN_TCGEN05_V2),
+                        ("tcgen05_v2_tmemP", _lib.ATTN_TCGEN05_V2_PTMEM), ("tcgen05_v2_3pipe", _lib.ATTN_TCGEN05_V2_3PIPE)):
         tower._attn_impl = impl
         errs[name_] = G.rel_err(tower(imgs.cuda()).cpu(), want)
     print(f"{cname}: default attention {e1:.3e}, others {errs}")
