@@ -7,14 +7,14 @@ bash scripts/gpu_diag.sh "$@"
 echo "=== smoke" | tee -a gpurun_out/diag_summary.txt
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | tee -a gpurun_out/diag_summary.txt
 echo "=== bench" | tee -a gpurun_out/diag_summary.txt
-timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -3 gpurun_out/bench.err; cat gpurun_out/bench.json | tee -a gpurun_out/diag_summary.txt
+timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -3 gpurun_out/bench.err; cat gpurun_out/bench.json | tee -a gpurun_out/diag_summary.txt
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; cat gpurun_out/bench_ref.json | tee -a gpurun_out/diag_summary.txt
 echo "=== kernels" | tee -a gpurun_out/diag_summary.txt
 timeout 300 python scripts/bench_kernels.py 64 2>&1 | tee gpurun_out/bench_kernels.log | tee -a gpurun_out/diag_summary.txt
 echo "=== ncu launches"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 170 -c 400 --csv --log-file gpurun_out/launches.csv \
-  python bench.py --steps 1 --warmup 1 --batch 64 --no-cpu-baseline --no-a-score > gpurun_out/ncu_launches.log 2>&1
+  python bench.py --steps 1 --warmup 1 --batch 128 --no-cpu-baseline --no-a-score > gpurun_out/ncu_launches.log 2>&1
 echo "=== ncu full"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'gemm_tcgen05|attention_tcgen05' -s 40 -c 6 -f -o gpurun_out/prof_gemm_attn \
-  python bench.py --steps 1 --warmup 1 --batch 64 --no-cpu-baseline --no-a-score > gpurun_out/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'gemm_tcgen05|attention2_tcgen05|layernorm' -s 40 -c 8 -f -o gpurun_out/prof_gemm_attn \
+  python bench.py --steps 1 --warmup 1 --batch 128 --no-cpu-baseline --no-a-score > gpurun_out/ncu_full.log 2>&1
 ls -la gpurun_out | tail -20
