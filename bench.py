@@ -218,7 +218,7 @@ def main():
         ga = torch.Generator(device=dev).manual_seed(11 + rank)
         o = torch.randn(hi - lo, T_PATCH, D, generator=ga, device=dev).to(torch.bfloat16)
         r_ = (0.5 * o.float() + torch.randn(hi - lo, T_PATCH, D, generator=ga, device=dev)).to(torch.bfloat16)
-        A.a_score_pairs(o[:64], r_[:64])
+        A.a_score_pairs(o, r_)                       # same shapes as the timed call: workspace allocation happens here
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -233,7 +233,7 @@ def main():
         a_info = dict(config="A-score max-cos over 10k x 576 x 1024 bf16 pairs (configs[2])", seconds=a_ms.item() / 1e3,
                       mean_a=s.item() / n_pairs, hbm_gbs=2 * n_pairs * T_PATCH * D * 2 / (a_ms.item() / 1e3) / 1e9 / world)
         # ---- linear CKA over the same rows (north_star metric; builder-defined): per-shard Gram, one all-reduce
-        CK.linear_cka(o[:8], r_[:8])
+        CK.linear_cka(o[:512], r_[:512])
         barrier()
         e0.record()
         gram, nrows, dx, dy = CK.cka_gram(o, r_)
@@ -256,7 +256,7 @@ def main():
         d1 = torch.randn(npairs_kp, Pg * Pg, D, generator=g5, device=dev).to(torch.bfloat16)
         d2 = torch.randn(npairs_kp, Pg * Pg, D, generator=g5, device=dev).to(torch.bfloat16)
         idx = torch.randint(0, Pg * Pg, (npairs_kp, K), generator=g5, device=dev).cpu().numpy()
-        CS.get_flow(d1[:2], d2[:2]); CS.keypoint_transformation(d1[:2], d2[:2], idx[:2])
+        CS.get_flow(d1[:npairs_dense], d2[:npairs_dense]); CS.keypoint_transformation(d1, d2, idx)   # warm-up, same shapes
         barrier()
         e0.record(); CS.get_flow(d1[:npairs_dense], d2[:npairs_dense]); e1.record(); barrier()
         dense_ms = e0.elapsed_time(e1)
@@ -287,7 +287,10 @@ def main():
                      api="extract.FeatureExtractor.run (pinned host pixels -> device -> pinned host features)"),
             roofline=dict(bound="tensor", kernel="gemm_tcgen05_kernel (all dense layers)", achieved=achieved,
                           peak=peaks["tflops"], unit="TFLOP/s", frac=achieved / peaks["tflops"], peak_source=peaks["source"],
-                          launches=gemm_launches, gemm_share_of_step=gemm_ms / ms, traffic=None,
+                          launches=gemm_launches, gemm_share_of_step=gemm_ms / ms,
+                          traffic=(792e6 if args.chunk == 128 else None),
+                          traffic_note="avg DRAM read+write bytes per dense-layer GEMM launch at 128 images (ncu --set full, "
+                                       "profiles/r01_ncu_summary_final.md)",
                           whole_step_tflops=value / world * FLOPS_PER_IMAGE / 1e12),
         )
         if a_info:
