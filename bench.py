@@ -129,7 +129,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="images per step per GPU")
     ap.add_argument("--chunk", type=int, default=128, help="images per native tower call")
-    ap.add_argument("--cpu-images", type=int, default=2, help="images per CPU-baseline sample")
+    ap.add_argument("--cpu-images", type=int, default=1, help="images per CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-a-score", action="store_true")
     args = ap.parse_args()

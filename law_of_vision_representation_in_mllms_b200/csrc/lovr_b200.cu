@@ -376,6 +376,8 @@ struct lovr_tower {
   float* x;      // [B*T, D] fp32 residual stream
   void* ln;      // [B*T, D] bf16: LayerNorm output / attention output
   void* big;     // [B*T, I] bf16: qkv (first 3D columns' worth) or MLP hidden; patch-embed scratch
+  cudaStream_t aux_stream = nullptr;  // second half-batch (created on first use)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 namespace {
@@ -398,7 +400,7 @@ WsLayout ws_layout(const lovr_tower_config& c, int B) {
                     static_cast<size_t>(B) * G * G * c.hidden_size * 4;
   if (qkv > big) big = qkv;
   if (pe > big) big = pe;
-  off += align_up(big, 1024);
+  off += align_up(big, 1024) + 2048;  // slack: the second half-batch's slice starts at a 1024-aligned offset
   l.total = off;
   return l;
 }
@@ -477,81 +479,153 @@ int lovr_tower_create(lovr_tower_t** out, const lovr_tower_config* cfg, const lo
   return 0;
 }
 
-void lovr_tower_destroy(lovr_tower_t* t) { delete t; }
+void lovr_tower_destroy(lovr_tower_t* t) {
+  if (!t) return;
+  if (t->aux_stream) cudaStreamDestroy(t->aux_stream);
+  if (t->ev_fork) cudaEventDestroy(t->ev_fork);
+  if (t->ev_join) cudaEventDestroy(t->ev_join);
+  delete t;
+}
+
+namespace {
+// One contiguous range of images of a forward call, with its own slice of the workspace and its own stream.
+struct Range {
+  int n0, n;
+  cudaStream_t s;
+  const void* pixels;
+  void* out;
+  float* x;
+  void* ln;
+  void* big;
+};
+size_t dtype_bytes(int dt) { return dt == LOVR_DT_F32 ? 4 : 2; }
+
+int tower_embed(lovr_tower_t* t, const Range& r, int pixel_dtype) {
+  using namespace lovr;
+  const lovr_tower_config& c = t->cfg;
+  const int D = c.hidden_size, T = t->T, G = t->G;
+  const bool f16 = c.operand_dtype == LOVR_DT_F16;
+  const int M = r.n * T, Mp = r.n * G * G;
+  int rc;
+  void* cols = r.big;
+  float* patch_out = reinterpret_cast<float*>(static_cast<uint8_t*>(r.big) +
+                                              align_up(static_cast<size_t>(Mp) * c.patch_k_padded * 2, 1024));
+  if ((rc = launch_im2col(r.pixels, pixel_dtype, cols, r.n, c.image_size, c.patch_size, c.patch_k_padded, f16, r.s))) return rc;
+  if ((rc = dense_gemm(cols, c.patch_k_padded, t->w.patch_w, c.patch_k_padded, patch_out, D, Mp, D, c.patch_k_padded,
+                       EPI_F32, ACT_NONE, f16, t->w.patch_b, nullptr, r.s)))
+    return rc;
+  const int wpb = 8;
+  const unsigned grid = static_cast<unsigned>((static_cast<size_t>(M) + wpb - 1) / wpb);
+  rc = dispatch_width(
+      D,
+      [&] {
+        embed_finalize_kernel<8><<<grid, wpb * 32, 0, r.s>>>(patch_out, t->w.cls, t->w.pos, t->w.pre_ln_w, t->w.pre_ln_b,
+                                                             c.ln_eps, r.x, r.n, T, c.has_cls);
+        return 0;
+      },
+      [&] {
+        embed_finalize_kernel<6><<<grid, wpb * 32, 0, r.s>>>(patch_out, t->w.cls, t->w.pos, t->w.pre_ln_w, t->w.pre_ln_b,
+                                                             c.ln_eps, r.x, r.n, T, c.has_cls);
+        return 0;
+      });
+  if (rc) return rc;
+  LAUNCH_CHECK("embed_finalize_kernel");
+  return 0;
+}
+
+// step 0..6 of one encoder layer for one range (so two ranges can be enqueued op by op on their streams)
+int tower_layer_step(lovr_tower_t* t, const Range& r, int li, int step, int attn_impl) {
+  using namespace lovr;
+  const lovr_tower_config& c = t->cfg;
+  const int D = c.hidden_size, I = c.intermediate_size, T = t->T;
+  const bool f16 = c.operand_dtype == LOVR_DT_F16;
+  const int M = r.n * T;
+  const lovr_layer_weights& lw = t->layers[li];
+  switch (step) {
+    case 0: return launch_layernorm(r.x, lw.ln1_w, lw.ln1_b, c.ln_eps, r.ln, M, D, f16, r.s);
+    case 1: return dense_gemm(r.ln, D, lw.qkv_w, D, r.big, 3 * D, M, 3 * D, D, EPI_BF16, ACT_NONE, f16, lw.qkv_b, nullptr, r.s);
+    case 2: return launch_attention(r.big, r.ln, r.n, T, c.num_heads, attn_impl, f16, r.s);
+    case 3: return dense_gemm(r.ln, D, lw.o_w, D, r.x, D, M, D, D, EPI_RESID_F32, ACT_NONE, f16, lw.o_b, lw.ls1, r.s);
+    case 4: return launch_layernorm(r.x, lw.ln2_w, lw.ln2_b, c.ln_eps, r.ln, M, D, f16, r.s);
+    case 5: return dense_gemm(r.ln, D, lw.fc1_w, D, r.big, I, M, I, D, EPI_BF16, c.act, f16, lw.fc1_b, nullptr, r.s);
+    default: return dense_gemm(r.big, I, lw.fc2_w, I, r.x, D, M, D, I, EPI_RESID_F32, ACT_NONE, f16, lw.fc2_b, lw.ls2, r.s);
+  }
+}
+
+int tower_finish(lovr_tower_t* t, const Range& r, int drop, int out_dtype, int64_t out_ld, int64_t out_col_off) {
+  using namespace lovr;
+  const int D = t->cfg.hidden_size, T = t->T;
+  const size_t rows = static_cast<size_t>(r.n) * (T - drop);
+  const int wpb = 8;
+  const unsigned grid = static_cast<unsigned>((rows + wpb - 1) / wpb);
+  int rc = dispatch_width(
+      D,
+      [&] {
+        select_cast_kernel<8><<<grid, wpb * 32, 0, r.s>>>(r.x, r.out, out_dtype, r.n, T, drop, static_cast<int>(out_ld),
+                                                          static_cast<int>(out_col_off));
+        return 0;
+      },
+      [&] {
+        select_cast_kernel<6><<<grid, wpb * 32, 0, r.s>>>(r.x, r.out, out_dtype, r.n, T, drop, static_cast<int>(out_ld),
+                                                          static_cast<int>(out_col_off));
+        return 0;
+      });
+  if (rc) return rc;
+  LAUNCH_CHECK("select_cast_kernel");
+  return 0;
+}
+}  // namespace
 
 int lovr_tower_forward(lovr_tower_t* t, const void* pixels, int32_t pixel_dtype, int32_t n_img, int32_t layers_to_run,
                        int32_t drop_first, void* out, int32_t out_dtype, int64_t out_ld, int64_t out_col_off,
                        int32_t attn_impl, void* stream) {
-  using namespace lovr;
   if (!t || !pixels || !out) return fail(LOVR_E_ARG, "tower_forward: null argument");
   if (n_img <= 0 || n_img > t->max_batch) return fail(LOVR_E_ARG, "n_img=%d outside [1,%d]", n_img, t->max_batch);
   if (layers_to_run < 0 || layers_to_run > t->cfg.num_layers) return fail(LOVR_E_ARG, "layers_to_run=%d", layers_to_run);
   const lovr_tower_config& c = t->cfg;
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int D = c.hidden_size, I = c.intermediate_size, T = t->T, G = t->G;
-  const bool f16 = c.operand_dtype == LOVR_DT_F16;
-  const int M = n_img * T;
-  const int Mp = n_img * G * G;
+  cudaStream_t s0 = static_cast<cudaStream_t>(stream);
+  const int D = c.hidden_size, I = c.intermediate_size, T = t->T;
+  const int drop = drop_first ? 1 : 0;
+  // Two half-batches on two streams: the HBM-bound kernels of one half (LayerNorm, im2col, select) co-run with the
+  // persistent tensor-core GEMM of the other half (the GEMM CTA leaves thread/register room on every SM); no data is
+  // shared between the halves, so the only synchronisation is fork/join on the caller's stream.
+  static const int kStreams = [] { const char* e = getenv("LOVR_TOWER_STREAMS"); return e ? atoi(e) : 2; }();
+  const int nr = (kStreams >= 2 && n_img >= 16) ? 2 : 1;
+  if (nr == 2 && !t->aux_stream) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&t->aux_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&t->ev_join, cudaEventDisableTiming));
+  }
+  Range rg[2];
+  const size_t px_img = static_cast<size_t>(3) * c.image_size * c.image_size * dtype_bytes(pixel_dtype);
+  const size_t out_img = static_cast<size_t>(T - drop) * out_ld * dtype_bytes(out_dtype);
+  for (int i = 0; i < nr; ++i) {
+    const int n0 = i == 0 ? 0 : n_img / 2;
+    const int n1 = (nr == 1) ? n_img : (i == 0 ? n_img / 2 : n_img);
+    rg[i].n0 = n0; rg[i].n = n1 - n0;
+    rg[i].s = i == 0 ? s0 : t->aux_stream;
+    rg[i].pixels = static_cast<const uint8_t*>(pixels) + n0 * px_img;
+    rg[i].out = static_cast<uint8_t*>(out) + n0 * out_img;
+    rg[i].x = t->x + static_cast<size_t>(n0) * T * D;
+    rg[i].ln = static_cast<uint8_t*>(t->ln) + static_cast<size_t>(n0) * T * D * 2;
+    rg[i].big = static_cast<uint8_t*>(t->big) + align_up(static_cast<size_t>(n0) * T * I * 2, 1024);
+  }
+  if (nr == 2) {
+    CUDA_TRY(cudaEventRecord(t->ev_fork, s0));
+    CUDA_TRY(cudaStreamWaitEvent(t->aux_stream, t->ev_fork, 0));
+  }
   int rc;
-  // ---- embeddings: im2col -> GEMM (+conv bias) -> +cls, +pos, (pre-LN)
-  void* cols = t->big;
-  float* patch_out = reinterpret_cast<float*>(static_cast<uint8_t*>(t->big) +
-                                              align_up(static_cast<size_t>(Mp) * c.patch_k_padded * 2, 1024));
-  if ((rc = launch_im2col(pixels, pixel_dtype, cols, n_img, c.image_size, c.patch_size, c.patch_k_padded, f16, s))) return rc;
-  if ((rc = dense_gemm(cols, c.patch_k_padded, t->w.patch_w, c.patch_k_padded, patch_out, D, Mp, D, c.patch_k_padded,
-                       EPI_F32, ACT_NONE, f16, t->w.patch_b, nullptr, s)))
-    return rc;
-  {
-    const int wpb = 8;
-    const unsigned grid = static_cast<unsigned>((static_cast<size_t>(M) + wpb - 1) / wpb);
-    rc = dispatch_width(
-        D,
-        [&] {
-          embed_finalize_kernel<8><<<grid, wpb * 32, 0, s>>>(patch_out, t->w.cls, t->w.pos, t->w.pre_ln_w, t->w.pre_ln_b,
-                                                             c.ln_eps, t->x, n_img, T, c.has_cls);
-          return 0;
-        },
-        [&] {
-          embed_finalize_kernel<6><<<grid, wpb * 32, 0, s>>>(patch_out, t->w.cls, t->w.pos, t->w.pre_ln_w, t->w.pre_ln_b,
-                                                             c.ln_eps, t->x, n_img, T, c.has_cls);
-          return 0;
-        });
-    if (rc) return rc;
-    LAUNCH_CHECK("embed_finalize_kernel");
-  }
-  // ---- encoder layers
-  for (int li = 0; li < layers_to_run; ++li) {
-    const lovr_layer_weights& lw = t->layers[li];
-    if ((rc = launch_layernorm(t->x, lw.ln1_w, lw.ln1_b, c.ln_eps, t->ln, M, D, f16, s))) return rc;
-    if ((rc = dense_gemm(t->ln, D, lw.qkv_w, D, t->big, 3 * D, M, 3 * D, D, EPI_BF16, ACT_NONE, f16, lw.qkv_b, nullptr, s)))
-      return rc;
-    if ((rc = launch_attention(t->big, t->ln, n_img, T, c.num_heads, attn_impl, f16, s))) return rc;
-    if ((rc = dense_gemm(t->ln, D, lw.o_w, D, t->x, D, M, D, D, EPI_RESID_F32, ACT_NONE, f16, lw.o_b, lw.ls1, s))) return rc;
-    if ((rc = launch_layernorm(t->x, lw.ln2_w, lw.ln2_b, c.ln_eps, t->ln, M, D, f16, s))) return rc;
-    if ((rc = dense_gemm(t->ln, D, lw.fc1_w, D, t->big, I, M, I, D, EPI_BF16, c.act, f16, lw.fc1_b, nullptr, s))) return rc;
-    if ((rc = dense_gemm(t->big, I, lw.fc2_w, I, t->x, D, M, D, I, EPI_RESID_F32, ACT_NONE, f16, lw.fc2_b, lw.ls2, s)))
-      return rc;
-  }
-  // ---- feature_select + cast into the caller's layout
-  {
-    const int drop = drop_first ? 1 : 0;
-    const size_t rows = static_cast<size_t>(n_img) * (T - drop);
-    const int wpb = 8;
-    const unsigned grid = static_cast<unsigned>((rows + wpb - 1) / wpb);
-    rc = dispatch_width(
-        D,
-        [&] {
-          select_cast_kernel<8><<<grid, wpb * 32, 0, s>>>(t->x, out, out_dtype, n_img, T, drop, static_cast<int>(out_ld),
-                                                          static_cast<int>(out_col_off));
-          return 0;
-        },
-        [&] {
-          select_cast_kernel<6><<<grid, wpb * 32, 0, s>>>(t->x, out, out_dtype, n_img, T, drop, static_cast<int>(out_ld),
-                                                          static_cast<int>(out_col_off));
-          return 0;
-        });
-    if (rc) return rc;
-    LAUNCH_CHECK("select_cast_kernel");
+  for (int i = 0; i < nr; ++i)
+    if ((rc = tower_embed(t, rg[i], pixel_dtype))) return rc;
+  for (int li = 0; li < layers_to_run; ++li)
+    for (int step = 0; step < 7; ++step)
+      for (int i = 0; i < nr; ++i)
+        if ((rc = tower_layer_step(t, rg[i], li, step, attn_impl))) return rc;
+  for (int i = 0; i < nr; ++i)
+    if ((rc = tower_finish(t, rg[i], drop, out_dtype, out_ld, out_col_off))) return rc;
+  if (nr == 2) {
+    CUDA_TRY(cudaEventRecord(t->ev_join, t->aux_stream));
+    CUDA_TRY(cudaStreamWaitEvent(s0, t->ev_join, 0));
   }
   return 0;
 }
