@@ -586,10 +586,11 @@ int lovr_tower_forward(lovr_tower_t* t, const void* pixels, int32_t pixel_dtype,
   cudaStream_t s0 = static_cast<cudaStream_t>(stream);
   const int D = c.hidden_size, I = c.intermediate_size, T = t->T;
   const int drop = drop_first ? 1 : 0;
-  // Two half-batches on two streams: the HBM-bound kernels of one half (LayerNorm, im2col, select) co-run with the
-  // persistent tensor-core GEMM of the other half (the GEMM CTA leaves thread/register room on every SM); no data is
-  // shared between the halves, so the only synchronisation is fork/join on the caller's stream.
-  static const int kStreams = [] { const char* e = getenv("LOVR_TOWER_STREAMS"); return e ? atoi(e) : 2; }();
+  // Optional (LOVR_TOWER_STREAMS=2): two half-batches on two streams, so the HBM-bound kernels of one half (LayerNorm,
+  // im2col, select) can co-run with the persistent tensor-core GEMM of the other half.  Measured on B200: no gain
+  // (2326 vs 2322 images/s) — the step runs at the 1000 W power cap (sw_power_cap, ~1.55 GHz), so overlapping more work
+  // only lowers the clock.  Default is therefore one stream, which also keeps the live GEMM timing of bench.py clean.
+  static const int kStreams = [] { const char* e = getenv("LOVR_TOWER_STREAMS"); return e ? atoi(e) : 1; }();
   const int nr = (kStreams >= 2 && n_img >= 16) ? 2 : 1;
   if (nr == 2 && !t->aux_stream) {
     CUDA_TRY(cudaStreamCreateWithFlags(&t->aux_stream, cudaStreamNonBlocking));
