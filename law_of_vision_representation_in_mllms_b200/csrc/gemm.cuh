@@ -71,6 +71,158 @@ __device__ __forceinline__ float apply_act(float x) {
   return x;
 }
 
+// Epilogue of one 128-row x BN-column accumulator tile for one epilogue warp (its 32 TMEM lanes = 32 output rows):
+// shared by the 1-CTA and the 2-CTA (cta_group::2) kernels.
+template <int BN, int EPI, int ACT, bool F16>
+__device__ __forceinline__ void epilogue_tile(const uint32_t t_row, const int col_tile, const int row0, const int b,
+                                              const GemmArgs& p, const CUtensorMap& tmC, uint8_t* my_stage,
+                                              uint64_t* my_rbar, const int lane, const uint32_t row_sw, uint32_t& g,
+                                              float& run_max) {
+    if constexpr (EPI == EPI_BF16) {
+      constexpr int CH = 64;
+#pragma unroll 1
+      for (int c = 0; c < BN / CH; ++c, ++g) {
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32b_x32(t_row + c * CH, r0);
+        tmem_ld_32x32b_x32(t_row + c * CH + 32, r1);
+        uint8_t* buf = my_stage + (g & 1) * kStageBufBytes;
+        if (lane == 0) tma_store_wait_read<1>();  // the store issued 2 chunks ago has drained this buffer
+        __syncwarp();
+        tmem_ld_wait();
+        const int col0 = col_tile + c * CH;
+        const uint32_t buf_row = smem_u32(buf) + lane * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float v[8];
+          float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+          if (p.bias) {
+            b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j * 8));
+            b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j * 8 + 4));
+          }
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int cc = j * 8 + e;
+            const float x = __uint_as_float(cc < 32 ? r0[cc] : r1[cc - 32]) + bb[e];
+            v[e] = apply_act<ACT>(x);
+          }
+          st_shared_v4(buf_row + ((j ^ row_sw) << 4), pack16x2<F16>(v[0], v[1]), pack16x2<F16>(v[2], v[3]),
+                       pack16x2<F16>(v[4], v[5]), pack16x2<F16>(v[6], v[7]));
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&tmC, buf, col0, row0, b);
+          tma_store_commit();
+        }
+      }
+    } else if constexpr (EPI == EPI_F32) {
+      constexpr int CH = 32;
+#pragma unroll 1
+      for (int c = 0; c < BN / CH; ++c, ++g) {
+        uint32_t r0[32];
+        tmem_ld_32x32b_x32(t_row + c * CH, r0);
+        uint8_t* buf = my_stage + (g & 1) * kStageBufBytes;
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+        tmem_ld_wait();
+        const int col0 = col_tile + c * CH;
+        const uint32_t buf_row = smem_u32(buf) + lane * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float v[4];
+          float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias) b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j * 4));
+          const float bb[4] = {b0.x, b0.y, b0.z, b0.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[e] = __uint_as_float(r0[j * 4 + e]) + bb[e];
+          if (p.colscale) {  // similarity GEMMs: C = rowscale[b,row] * colscale[b,col] * acc (padded to BN)
+            const float4 s0 =
+                __ldg(reinterpret_cast<const float4*>(p.colscale + static_cast<size_t>(b) * p.scale_ld + col0 + j * 4));
+            const float rs = __ldg(p.rowscale + static_cast<size_t>(b) * p.scale_ld + min(row0 + lane, p.M - 1));
+            v[0] *= s0.x * rs;
+            v[1] *= s0.y * rs;
+            v[2] *= s0.z * rs;
+            v[3] *= s0.w * rs;
+          }
+          st_shared_v4(buf_row + ((j ^ row_sw) << 4), __float_as_uint(v[0]), __float_as_uint(v[1]),
+                       __float_as_uint(v[2]), __float_as_uint(v[3]));
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&tmC, buf, col0, row0, b);
+          tma_store_commit();
+        }
+      }
+    } else if constexpr (EPI == EPI_RESID_F32) {
+      constexpr int CH = 32;
+      constexpr int NCH = BN / CH;
+      // prefetch residual chunk 0 of this tile
+      if (lane == 0) {
+        tma_store_wait_read<0>();
+        uint8_t* buf = my_stage + (g & 1) * kStageBufBytes;
+        mbar_arrive_expect_tx(&my_rbar[g & 1], kStageBufBytes);
+        tma_load_3d(buf, &tmC, &my_rbar[g & 1], col_tile, row0, b);
+      }
+#pragma unroll 1
+      for (int c = 0; c < NCH; ++c, ++g) {
+        uint32_t r0[32];
+        tmem_ld_32x32b_x32(t_row + c * CH, r0);
+        if (lane == 0 && c + 1 < NCH) {
+          // buffer (g+1)&1 was last read by the store of chunk g-1
+          tma_store_wait_read<0>();
+          uint8_t* nbuf = my_stage + ((g + 1) & 1) * kStageBufBytes;
+          mbar_arrive_expect_tx(&my_rbar[(g + 1) & 1], kStageBufBytes);
+          tma_load_3d(nbuf, &tmC, &my_rbar[(g + 1) & 1], col_tile + (c + 1) * CH, row0, b);
+        }
+        uint8_t* buf = my_stage + (g & 1) * kStageBufBytes;
+        mbar_wait(&my_rbar[g & 1], (g >> 1) & 1);
+        tmem_ld_wait();
+        const int col0 = col_tile + c * CH;
+        const uint32_t buf_row = smem_u32(buf) + lane * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint32_t q0, q1, q2, q3;
+          const uint32_t addr = buf_row + ((j ^ row_sw) << 4);
+          ld_shared_v4(addr, q0, q1, q2, q3);
+          float res[4] = {__uint_as_float(q0), __uint_as_float(q1), __uint_as_float(q2), __uint_as_float(q3)};
+          float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), s0 = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (p.bias) b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j * 4));
+          if (p.colscale) s0 = __ldg(reinterpret_cast<const float4*>(p.colscale + col0 + j * 4));
+          const float bb[4] = {b0.x, b0.y, b0.z, b0.w};
+          const float ss[4] = {s0.x, s0.y, s0.z, s0.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) res[e] += (__uint_as_float(r0[j * 4 + e]) + bb[e]) * ss[e];
+          st_shared_v4(addr, __float_as_uint(res[0]), __float_as_uint(res[1]), __float_as_uint(res[2]),
+                       __float_as_uint(res[3]));
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&tmC, buf, col0, row0, b);
+          tma_store_commit();
+        }
+      }
+    } else {  // EPI_ROWMAX
+      constexpr int CH = 32;
+      const float* cs = p.colscale + static_cast<size_t>(b) * p.N;
+#pragma unroll 1
+      for (int c = 0; c < BN / CH; ++c) {
+        const int col0 = col_tile + c * CH;
+        if (col0 >= p.n_valid) break;  // warp-uniform
+        uint32_t r0[32];
+        tmem_ld_32x32b_x32(t_row + c * CH, r0);
+        tmem_ld_wait();
+#pragma unroll
+        for (int cc = 0; cc < 32; ++cc) {
+          const float x = __uint_as_float(r0[cc]) * __ldg(cs + min(col0 + cc, p.N - 1));
+          if (col0 + cc < p.n_valid) run_max = fmaxf(run_max, x);
+        }
+      }
+    }
+}
+
 template <int BN, int EPI, int ACT, bool F16>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -209,149 +361,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tc_fence_after();
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
 
-        if constexpr (EPI == EPI_BF16) {
-          constexpr int CH = 64;
-#pragma unroll 1
-          for (int c = 0; c < BN / CH; ++c, ++g) {
-            uint32_t r0[32], r1[32];
-            tmem_ld_32x32b_x32(t_row + c * CH, r0);
-            tmem_ld_32x32b_x32(t_row + c * CH + 32, r1);
-            uint8_t* buf = my_stage + (g & 1) * kStageBufBytes;
-            if (lane == 0) tma_store_wait_read<1>();  // the store issued 2 chunks ago has drained this buffer
-            __syncwarp();
-            tmem_ld_wait();
-            const int col0 = col_tile + c * CH;
-            const uint32_t buf_row = smem_u32(buf) + lane * 128;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float v[8];
-              float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-              if (p.bias) {
-                b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j * 8));
-                b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j * 8 + 4));
-              }
-              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const int cc = j * 8 + e;
-                const float x = __uint_as_float(cc < 32 ? r0[cc] : r1[cc - 32]) + bb[e];
-                v[e] = apply_act<ACT>(x);
-              }
-              st_shared_v4(buf_row + ((j ^ row_sw) << 4), pack16x2<F16>(v[0], v[1]), pack16x2<F16>(v[2], v[3]),
-                           pack16x2<F16>(v[4], v[5]), pack16x2<F16>(v[6], v[7]));
-            }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_3d(&tmC, buf, col0, row0, b);
-              tma_store_commit();
-            }
-          }
-        } else if constexpr (EPI == EPI_F32) {
-          constexpr int CH = 32;
-#pragma unroll 1
-          for (int c = 0; c < BN / CH; ++c, ++g) {
-            uint32_t r0[32];
-            tmem_ld_32x32b_x32(t_row + c * CH, r0);
-            uint8_t* buf = my_stage + (g & 1) * kStageBufBytes;
-            if (lane == 0) tma_store_wait_read<1>();
-            __syncwarp();
-            tmem_ld_wait();
-            const int col0 = col_tile + c * CH;
-            const uint32_t buf_row = smem_u32(buf) + lane * 128;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float v[4];
-              float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (p.bias) b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j * 4));
-              const float bb[4] = {b0.x, b0.y, b0.z, b0.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) v[e] = __uint_as_float(r0[j * 4 + e]) + bb[e];
-              if (p.colscale) {  // similarity GEMMs: C = rowscale[b,row] * colscale[b,col] * acc (padded to BN)
-                const float4 s0 =
-                    __ldg(reinterpret_cast<const float4*>(p.colscale + static_cast<size_t>(b) * p.scale_ld + col0 + j * 4));
-                const float rs = __ldg(p.rowscale + static_cast<size_t>(b) * p.scale_ld + min(row0 + lane, p.M - 1));
-                v[0] *= s0.x * rs;
-                v[1] *= s0.y * rs;
-                v[2] *= s0.z * rs;
-                v[3] *= s0.w * rs;
-              }
-              st_shared_v4(buf_row + ((j ^ row_sw) << 4), __float_as_uint(v[0]), __float_as_uint(v[1]),
-                           __float_as_uint(v[2]), __float_as_uint(v[3]));
-            }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_3d(&tmC, buf, col0, row0, b);
-              tma_store_commit();
-            }
-          }
-        } else if constexpr (EPI == EPI_RESID_F32) {
-          constexpr int CH = 32;
-          constexpr int NCH = BN / CH;
-          // prefetch residual chunk 0 of this tile
-          if (lane == 0) {
-            tma_store_wait_read<0>();
-            uint8_t* buf = my_stage + (g & 1) * kStageBufBytes;
-            mbar_arrive_expect_tx(&my_rbar[g & 1], kStageBufBytes);
-            tma_load_3d(buf, &tmC, &my_rbar[g & 1], col_tile, row0, b);
-          }
-#pragma unroll 1
-          for (int c = 0; c < NCH; ++c, ++g) {
-            uint32_t r0[32];
-            tmem_ld_32x32b_x32(t_row + c * CH, r0);
-            if (lane == 0 && c + 1 < NCH) {
-              // buffer (g+1)&1 was last read by the store of chunk g-1
-              tma_store_wait_read<0>();
-              uint8_t* nbuf = my_stage + ((g + 1) & 1) * kStageBufBytes;
-              mbar_arrive_expect_tx(&my_rbar[(g + 1) & 1], kStageBufBytes);
-              tma_load_3d(nbuf, &tmC, &my_rbar[(g + 1) & 1], col_tile + (c + 1) * CH, row0, b);
-            }
-            uint8_t* buf = my_stage + (g & 1) * kStageBufBytes;
-            mbar_wait(&my_rbar[g & 1], (g >> 1) & 1);
-            tmem_ld_wait();
-            const int col0 = col_tile + c * CH;
-            const uint32_t buf_row = smem_u32(buf) + lane * 128;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              uint32_t q0, q1, q2, q3;
-              const uint32_t addr = buf_row + ((j ^ row_sw) << 4);
-              ld_shared_v4(addr, q0, q1, q2, q3);
-              float res[4] = {__uint_as_float(q0), __uint_as_float(q1), __uint_as_float(q2), __uint_as_float(q3)};
-              float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), s0 = make_float4(1.f, 1.f, 1.f, 1.f);
-              if (p.bias) b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j * 4));
-              if (p.colscale) s0 = __ldg(reinterpret_cast<const float4*>(p.colscale + col0 + j * 4));
-              const float bb[4] = {b0.x, b0.y, b0.z, b0.w};
-              const float ss[4] = {s0.x, s0.y, s0.z, s0.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) res[e] += (__uint_as_float(r0[j * 4 + e]) + bb[e]) * ss[e];
-              st_shared_v4(addr, __float_as_uint(res[0]), __float_as_uint(res[1]), __float_as_uint(res[2]),
-                           __float_as_uint(res[3]));
-            }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_3d(&tmC, buf, col0, row0, b);
-              tma_store_commit();
-            }
-          }
-        } else {  // EPI_ROWMAX
-          constexpr int CH = 32;
-          const float* cs = p.colscale + static_cast<size_t>(b) * p.N;
-#pragma unroll 1
-          for (int c = 0; c < BN / CH; ++c) {
-            const int col0 = col_tile + c * CH;
-            if (col0 >= p.n_valid) break;  // warp-uniform
-            uint32_t r0[32];
-            tmem_ld_32x32b_x32(t_row + c * CH, r0);
-            tmem_ld_wait();
-#pragma unroll
-            for (int cc = 0; cc < 32; ++cc) {
-              const float x = __uint_as_float(r0[cc]) * __ldg(cs + min(col0 + cc, p.N - 1));
-              if (col0 + cc < p.n_valid) run_max = fmaxf(run_max, x);
-            }
-          }
-        }
+        epilogue_tile<BN, EPI, ACT, F16>(t_row, col_tile, row0, b, p, tmC, my_stage, my_rbar, lane, row_sw, g, run_max);
         // all TMEM reads of this accumulator are complete (tcgen05.wait::ld above)
         tc_fence_before();
         __syncwarp();

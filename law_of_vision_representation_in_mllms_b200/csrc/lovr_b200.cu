@@ -20,6 +20,7 @@
 #include "cka.cuh"
 #include "cscore.cuh"
 #include "gemm.cuh"
+#include "gemm2.cuh"
 #include "rowwise.cuh"
 #include "scores.cuh"
 
@@ -215,6 +216,49 @@ int launch_gemm(int bn, int epi, int act, bool f16, const CUtensorMap& a, const 
 
 constexpr int kDenseBN = 256;
 
+template <int EPI, int ACT, bool F16>
+int launch_gemm2_inst(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const lovr::GemmArgs& args,
+                      cudaStream_t s) {
+  auto kern = lovr::gemm2_tcgen05_kernel<EPI, ACT, F16>;
+  static bool attr_set = false;
+  const int smem = lovr::Gemm2Smem::kTotal;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  const int units = ((args.M + 255) / 256) * (args.N / 256);
+  int grid = 2 * units < device_info().sms ? 2 * units : (device_info().sms & ~1);
+  if (grid <= 0) return 0;
+  size_t pidx = 0;
+  const bool profiled = prof_begin(s, 2.0 * args.M * args.N * static_cast<double>(args.K), &pidx);
+  kern<<<grid, lovr::kGemmThreads, smem, s>>>(a, b, c, args);  // __cluster_dims__(2,1,1) on the kernel
+  if (profiled) prof_end(s, pidx);
+  LAUNCH_CHECK("gemm2_tcgen05_kernel");
+  return 0;
+}
+
+int launch_gemm2(int epi, int act, bool f16, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c,
+                 const lovr::GemmArgs& args, cudaStream_t s) {
+  using namespace lovr;
+#define LOVR_GEMM2_CASE(EPI_, ACT_)                                                                     \
+  if (epi == EPI_ && act == ACT_)                                                                       \
+    return f16 ? launch_gemm2_inst<EPI_, ACT_, true>(a, b, c, args, s) : launch_gemm2_inst<EPI_, ACT_, false>(a, b, c, args, s);
+  LOVR_GEMM2_CASE(EPI_BF16, ACT_NONE)
+  LOVR_GEMM2_CASE(EPI_BF16, ACT_QUICK_GELU)
+  LOVR_GEMM2_CASE(EPI_BF16, ACT_GELU_ERF)
+  LOVR_GEMM2_CASE(EPI_BF16, ACT_GELU_TANH)
+  LOVR_GEMM2_CASE(EPI_RESID_F32, ACT_NONE)
+  LOVR_GEMM2_CASE(EPI_F32, ACT_NONE)
+#undef LOVR_GEMM2_CASE
+  return fail(LOVR_E_UNSUPPORTED, "gemm2: no instance for epi=%d act=%d", epi, act);
+}
+
+// 0 = 1-CTA kernel (cta_group::1), 1 = CTA-pair kernel (cta_group::2).  LOVR_GEMM_2CTA overrides the default.
+int gemm_use_pairs() {
+  const char* e = getenv("LOVR_GEMM_2CTA");
+  return e ? atoi(e) : 0;
+}
+
 // Dense layer: A [M,K] bf16 (lda), W [N,K] bf16 (ldw), C [M,N] (ldc; bf16 or fp32 by epilogue).
 int dense_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int M, int N, int K,
                int epi, int act, bool f16, const float* bias, const float* colscale, cudaStream_t s) {
@@ -223,7 +267,8 @@ int dense_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, 
   CUtensorMap ta, tb, tc;
   int rc;
   if ((rc = make_tmap(&ta, A, 2, K, M, 1, lda, static_cast<uint64_t>(lda) * M, 64, lovr::kBM))) return rc;
-  if ((rc = make_tmap(&tb, W, 2, K, N, 1, ldw, static_cast<uint64_t>(ldw) * N, 64, kDenseBN))) return rc;
+  const bool pairs = gemm_use_pairs() != 0 && M > 128;
+  if ((rc = make_tmap(&tb, W, 2, K, N, 1, ldw, static_cast<uint64_t>(ldw) * N, 64, pairs ? 128 : kDenseBN))) return rc;
   if (epi == lovr::EPI_BF16) {
     if ((rc = make_tmap(&tc, C, 2, N, M, 1, ldc, static_cast<uint64_t>(ldc) * M, 64, 32))) return rc;
   } else {
@@ -233,6 +278,7 @@ int dense_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, 
   g.M = M; g.N = N; g.K = K; g.batch = 1; g.n_inner = 1;
   g.bias = bias; g.colscale = colscale; g.rowscale = nullptr; g.rowmax = nullptr; g.n_valid = N; g.scale_ld = 0;
   if (epi == lovr::EPI_F32) g.colscale = nullptr;  // (similarity scaling is only used by the C-score path)
+  if (pairs) return launch_gemm2(epi, act, f16, ta, tb, tc, g, s);
   return launch_gemm(kDenseBN, epi, act, f16, ta, tb, tc, g, s);
 }
 
