@@ -277,6 +277,7 @@ int dense_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, 
   lovr::GemmArgs g{};
   g.M = M; g.N = N; g.K = K; g.batch = 1; g.n_inner = 1;
   g.bias = bias; g.colscale = colscale; g.rowscale = nullptr; g.rowmax = nullptr; g.n_valid = N; g.scale_ld = 0;
+  g.c_ptr = C; g.ldc = ldc; g.c_batch_stride = 0;
   if (epi == lovr::EPI_F32) g.colscale = nullptr;  // (similarity scaling is only used by the C-score path)
   if (pairs) return launch_gemm2(epi, act, f16, ta, tb, tc, g, s);
   return launch_gemm(kDenseBN, epi, act, f16, ta, tb, tc, g, s);
