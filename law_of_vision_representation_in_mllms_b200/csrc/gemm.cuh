@@ -168,59 +168,57 @@ __device__ __forceinline__ void epilogue_tile(const uint32_t t_row, const int co
         }
       }
     } else if constexpr (EPI == EPI_RESID_F32) {
-      // In-place residual update without TMA or async-proxy fences: the accumulator chunk goes through a swizzled smem
-      // transpose so that the read-modify-write of x is fully coalesced (8 lanes x 16 B = one 128-B row segment, 4 rows
-      // per instruction); the residual loads of a chunk are issued before its TMEM load so their latency is hidden.
-      // (The TMA load/store version paid a ~700-cycle fence.proxy.async per 32-column chunk: out-proj ran at 855 TFLOP/s.)
       constexpr int CH = 32;
       constexpr int NCH = BN / CH;
-      float* C = reinterpret_cast<float*>(p.c_ptr) + static_cast<size_t>(b) * p.c_batch_stride;
-      const int sub_row = lane >> 3, sub_chunk = lane & 7;
+      // prefetch residual chunk 0 of this tile
+      if (lane == 0) {
+        tma_store_wait_read<0>();
+        uint8_t* buf = my_stage + (g & 1) * kStageBufBytes;
+        mbar_arrive_expect_tx(&my_rbar[g & 1], kStageBufBytes);
+        tma_load_3d(buf, &tmC, &my_rbar[g & 1], col_tile, row0, b);
+      }
 #pragma unroll 1
       for (int c = 0; c < NCH; ++c, ++g) {
-        const int col0 = col_tile + c * CH;
-        float4 res[8];
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {  // residual x[row, col0 + 4*sub_chunk ..]: issued first, consumed last
-          const int row = row0 + it * 4 + sub_row;
-          res[it] = (row < p.M) ? *reinterpret_cast<const float4*>(C + static_cast<size_t>(row) * p.ldc + col0 + sub_chunk * 4)
-                                : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
         uint32_t r0[32];
         tmem_ld_32x32b_x32(t_row + c * CH, r0);
-        tmem_ld_wait();
+        if (lane == 0 && c + 1 < NCH) {
+          // buffer (g+1)&1 was last read by the store of chunk g-1
+          tma_store_wait_read<0>();
+          uint8_t* nbuf = my_stage + ((g + 1) & 1) * kStageBufBytes;
+          mbar_arrive_expect_tx(&my_rbar[(g + 1) & 1], kStageBufBytes);
+          tma_load_3d(nbuf, &tmC, &my_rbar[(g + 1) & 1], col_tile + (c + 1) * CH, row0, b);
+        }
         uint8_t* buf = my_stage + (g & 1) * kStageBufBytes;
-        const uint32_t buf_u = smem_u32(buf);
-        const uint32_t buf_row = buf_u + lane * 128;
+        mbar_wait(&my_rbar[g & 1], (g >> 1) & 1);
+        tmem_ld_wait();
+        const int col0 = col_tile + c * CH;
+        const uint32_t buf_row = smem_u32(buf) + lane * 128;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
+          uint32_t q0, q1, q2, q3;
+          const uint32_t addr = buf_row + ((j ^ row_sw) << 4);
+          ld_shared_v4(addr, q0, q1, q2, q3);
+          float res[4] = {__uint_as_float(q0), __uint_as_float(q1), __uint_as_float(q2), __uint_as_float(q3)};
           float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), s0 = make_float4(1.f, 1.f, 1.f, 1.f);
           if (p.bias) b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j * 4));
           if (p.colscale) s0 = __ldg(reinterpret_cast<const float4*>(p.colscale + col0 + j * 4));
-          st_shared_v4(buf_row + ((j ^ row_sw) << 4), __float_as_uint((__uint_as_float(r0[j * 4 + 0]) + b0.x) * s0.x),
-                       __float_as_uint((__uint_as_float(r0[j * 4 + 1]) + b0.y) * s0.y),
-                       __float_as_uint((__uint_as_float(r0[j * 4 + 2]) + b0.z) * s0.z),
-                       __float_as_uint((__uint_as_float(r0[j * 4 + 3]) + b0.w) * s0.w));
-        }
-        __syncwarp();
+          const float bb[4] = {b0.x, b0.y, b0.z, b0.w};
+          const float ss[4] = {s0.x, s0.y, s0.z, s0.w};
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int rr = it * 4 + sub_row;
-          const int row = row0 + rr;
-          uint32_t q0, q1, q2, q3;
-          ld_shared_v4(buf_u + rr * 128 + ((sub_chunk ^ (rr & 7)) << 4), q0, q1, q2, q3);
-          if (row < p.M) {
-            float4 o;
-            o.x = res[it].x + __uint_as_float(q0);
-            o.y = res[it].y + __uint_as_float(q1);
-            o.z = res[it].z + __uint_as_float(q2);
-            o.w = res[it].w + __uint_as_float(q3);
-            *reinterpret_cast<float4*>(C + static_cast<size_t>(row) * p.ldc + col0 + sub_chunk * 4) = o;
-          }
+          for (int e = 0; e < 4; ++e) res[e] += (__uint_as_float(r0[j * 4 + e]) + bb[e]) * ss[e];
+          st_shared_v4(addr, __float_as_uint(res[0]), __float_as_uint(res[1]), __float_as_uint(res[2]),
+                       __float_as_uint(res[3]));
         }
-        // the other staging buffer is used by the next chunk; this one is rewritten two chunks later, after the
-        // __syncwarp above of the next chunk has ordered these reads before those writes
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&tmC, buf, col0, row0, b);
+          tma_store_commit();
+        }
       }
+    // (A variant that replaced the TMA load/store of the residual chunk by a coalesced ld.global/st.global pass through
+    //  a shared-memory transpose — no async-proxy fences — was measured SLOWER: out-proj 685 vs 855 TFLOP/s, because the
+    //  residual loads then sit on the warp's critical path; the TMA version prefetches them one chunk ahead.)
     } else {  // EPI_ROWMAX
       constexpr int CH = 32;
       const float* cs = p.colscale + static_cast<size_t>(b) * p.N;
