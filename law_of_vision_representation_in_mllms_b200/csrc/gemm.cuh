@@ -85,7 +85,7 @@ __device__ __forceinline__ float apply_act(float x) {
 
 // Epilogue of one 128-row x BN-column accumulator tile for one epilogue warp (its 32 TMEM lanes = 32 output rows):
 // shared by the 1-CTA and the 2-CTA (cta_group::2) kernels.
-template <int BN, int EPI, int ACT, bool F16>
+template <int BN, int EPI, int ACT, bool F16, int RB = 2>  // RB: staging buffers per warp used by the residual epilogue
 __device__ __forceinline__ void epilogue_tile(const uint32_t t_row, const int col_tile, const int row0, const int b,
                                               const GemmArgs& p, const CUtensorMap& tmC, uint8_t* my_stage,
                                               uint64_t* my_rbar, const int lane, const uint32_t row_sw, uint32_t& g,
@@ -168,28 +168,37 @@ __device__ __forceinline__ void epilogue_tile(const uint32_t t_row, const int co
         }
       }
     } else if constexpr (EPI == EPI_RESID_F32) {
+      // x[row, col] += colscale * (acc + bias) in place.  The residual chunk (32 rows x 128 B) is TMA-loaded into the
+      // same swizzled staging buffer the result is stored from, PD chunks ahead of its use; with RB staging buffers per
+      // warp, PD = RB/2 loads and RB/2 stores are in flight.
       constexpr int CH = 32;
       constexpr int NCH = BN / CH;
-      // prefetch residual chunk 0 of this tile
+      constexpr int PD = RB / 2;
+      static_assert(RB == 2 || RB == 4, "residual staging depth");
       if (lane == 0) {
-        tma_store_wait_read<0>();
-        uint8_t* buf = my_stage + (g & 1) * kStageBufBytes;
-        mbar_arrive_expect_tx(&my_rbar[g & 1], kStageBufBytes);
-        tma_load_3d(buf, &tmC, &my_rbar[g & 1], col_tile, row0, b);
+        tma_store_wait_read<0>();  // tile boundary: every staging buffer of this warp is free again
+#pragma unroll
+        for (int i = 0; i < PD; ++i) {
+          const uint32_t gi = g + i;
+          uint8_t* buf = my_stage + (gi % RB) * kStageBufBytes;
+          mbar_arrive_expect_tx(&my_rbar[gi % RB], kStageBufBytes);
+          tma_load_3d(buf, &tmC, &my_rbar[gi % RB], col_tile + i * CH, row0, b);
+        }
       }
 #pragma unroll 1
       for (int c = 0; c < NCH; ++c, ++g) {
         uint32_t r0[32];
         tmem_ld_32x32b_x32(t_row + c * CH, r0);
-        if (lane == 0 && c + 1 < NCH) {
-          // buffer (g+1)&1 was last read by the store of chunk g-1
-          tma_store_wait_read<0>();
-          uint8_t* nbuf = my_stage + ((g + 1) & 1) * kStageBufBytes;
-          mbar_arrive_expect_tx(&my_rbar[(g + 1) & 1], kStageBufBytes);
-          tma_load_3d(nbuf, &tmC, &my_rbar[(g + 1) & 1], col_tile + (c + 1) * CH, row0, b);
+        if (lane == 0 && c + PD < NCH) {
+          // buffer (g+PD) % RB was last read by the store of chunk g+PD-RB: allow the PD-1 younger stores to stay in flight
+          tma_store_wait_read<PD - 1>();
+          const uint32_t gi = g + PD;
+          uint8_t* nbuf = my_stage + (gi % RB) * kStageBufBytes;
+          mbar_arrive_expect_tx(&my_rbar[gi % RB], kStageBufBytes);
+          tma_load_3d(nbuf, &tmC, &my_rbar[gi % RB], col_tile + (c + PD) * CH, row0, b);
         }
-        uint8_t* buf = my_stage + (g & 1) * kStageBufBytes;
-        mbar_wait(&my_rbar[g & 1], (g >> 1) & 1);
+        uint8_t* buf = my_stage + (g % RB) * kStageBufBytes;
+        mbar_wait(&my_rbar[g % RB], (g / RB) & 1);
         tmem_ld_wait();
         const int col0 = col_tile + c * CH;
         const uint32_t buf_row = smem_u32(buf) + lane * 128;

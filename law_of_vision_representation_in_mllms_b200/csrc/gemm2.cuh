@@ -16,14 +16,17 @@
 
 namespace lovr {
 
-constexpr int kStages2 = 6;
-
+// The residual epilogue trades one pipeline stage for a 4-deep staging ring per epilogue warp (two residual loads and two
+// stores in flight): it was the epilogue, not the main loop, that bounded the K=1024 out-projection.
+template <int EPI>
 struct Gemm2Smem {
+  static constexpr int kStages = (EPI == EPI_RESID_F32) ? 5 : 6;
+  static constexpr int kResidBufs = (EPI == EPI_RESID_F32) ? 4 : 2;
   static constexpr int kABytes = kBM * kBK * 2;        // 128 x 64 x 2
   static constexpr int kBBytes = 128 * kBK * 2;        // this CTA's half of the 256-row W tile
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagingBytes = kEpiWarps * 2 * kStageBufBytes;
-  static constexpr int kTotal = kStages2 * kStageBytes + kStagingBytes + 256 + 1024;
+  static constexpr int kStagingBytes = kEpiWarps * kResidBufs * kStageBufBytes;
+  static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + 512 + 1024;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -82,7 +85,9 @@ template <int EPI, int ACT, bool F16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmC, const GemmArgs p) {
-  using L = Gemm2Smem;
+  using L = Gemm2Smem<EPI>;
+  constexpr int kStages2 = L::kStages;
+  constexpr int RB = L::kResidBufs;
   constexpr int BN = 256;
   constexpr uint32_t kTmemCols = 512;
   constexpr uint32_t kIdesc = make_idesc_16(256, BN, 0, 0, F16);  // UMMA_M = 256 across the CTA pair
@@ -96,8 +101,8 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint64_t* empty_bar = bars + kStages2;           // [kStages2]
   uint64_t* tmem_full = bars + 2 * kStages2;       // [2]
   uint64_t* tmem_empty = bars + 2 * kStages2 + 2;  // [2]         (used in the leader)
-  uint64_t* resid_bar = bars + 2 * kStages2 + 4;   // [kEpiWarps][2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages2 + 4 + 2 * kEpiWarps);
+  uint64_t* resid_bar = bars + 2 * kStages2 + 4;   // [kEpiWarps][RB]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages2 + 4 + RB * kEpiWarps);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -122,7 +127,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 2 * kEpiWarps);
     }
-    for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&resid_bar[i], 1);
+    for (int i = 0; i < RB * kEpiWarps; ++i) mbar_init(&resid_bar[i], 1);
     fence_barrier_init();
   }
   cluster_sync_all();  // both CTAs' barriers exist before any remote signal
@@ -193,8 +198,8 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     // ===================================================================== epilogue warps (both CTAs)
     const int ew = warp - 2;
     const int quarter = warp & 3;
-    uint8_t* my_stage = staging + ew * 2 * kStageBufBytes;
-    uint64_t* my_rbar = resid_bar + ew * 2;
+    uint8_t* my_stage = staging + ew * RB * kStageBufBytes;
+    uint64_t* my_rbar = resid_bar + ew * RB;
     const uint32_t row_sw = (lane & 7);
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -207,7 +212,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-      epilogue_tile<BN, EPI, ACT, F16>(t_row, nt * BN, row0, 0, p, tmC, my_stage, my_rbar, lane, row_sw, g, run_max);
+      epilogue_tile<BN, EPI, ACT, F16, RB>(t_row, nt * BN, row0, 0, p, tmC, my_stage, my_rbar, lane, row_sw, g, run_max);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[acc]), 0));  // leader's barrier

@@ -221,7 +221,7 @@ int launch_gemm2_inst(const CUtensorMap& a, const CUtensorMap& b, const CUtensor
                       cudaStream_t s) {
   auto kern = lovr::gemm2_tcgen05_kernel<EPI, ACT, F16>;
   static bool attr_set = false;
-  const int smem = lovr::Gemm2Smem::kTotal;
+  const int smem = lovr::Gemm2Smem<EPI>::kTotal;
   if (!attr_set) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
