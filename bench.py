@@ -132,6 +132,8 @@ def main():
     ap.add_argument("--cpu-images", type=int, default=1, help="images per CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-a-score", action="store_true")
+    ap.add_argument("--operand-dtype", default="bf16", choices=["bf16", "fp16"],
+                    help="16-bit tensor-core operand format (fp32 accumulate either way)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -158,16 +160,17 @@ def main():
         torch.cuda.synchronize()
 
     ex = X.build_extractor(TOWER, chunk=args.chunk, lovr_max_batch=args.chunk, lovr_device=dev,
-                           lovr_state_dict=None, lovr_seed=0)
+                           lovr_state_dict=None, lovr_seed=0, lovr_operand_dtype=args.operand_dtype)
     tower = ex.towers[0]
     B = args.batch
     # ---- inputs: several distinct batches so every step reads pixels that are not L2-resident (B*677 KB >> L2 anyway)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     n_in = 3
-    dev_px = [torch.randn(B, 3, R, R, generator=g, device=dev).to(torch.bfloat16) for _ in range(n_in)]
-    dev_out = torch.empty(B, T_PATCH, D, dtype=torch.bfloat16, device=dev)
+    io_dtype = torch.bfloat16 if args.operand_dtype == "bf16" else torch.float16
+    dev_px = [torch.randn(B, 3, R, R, generator=g, device=dev).to(io_dtype) for _ in range(n_in)]
+    dev_out = torch.empty(B, T_PATCH, D, dtype=io_dtype, device=dev)
     host_px = [p.cpu().pin_memory() for p in dev_px[:2]]
-    host_out = torch.empty(B, T_PATCH, D, dtype=torch.bfloat16).pin_memory()
+    host_out = torch.empty(B, T_PATCH, D, dtype=io_dtype).pin_memory()
 
     def step_resident(i):
         tower.forward_into(dev_px[i % n_in], dev_out, 0)
@@ -274,7 +277,7 @@ def main():
         achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
         line = dict(
             metric=METRIC, value=value, unit="images/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
-            ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
+            ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype=args.operand_dtype,
             data="synthetic",
             config=dict(workload=WORKLOAD, tower=TOWER, images_per_step_per_gpu=B, native_chunk=args.chunk,
                         weights="seeded HF-init-style random weights (weights.synthetic_state_dict style=hf_init)",

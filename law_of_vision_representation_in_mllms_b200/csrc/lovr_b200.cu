@@ -253,10 +253,11 @@ int launch_gemm2(int epi, int act, bool f16, const CUtensorMap& a, const CUtenso
   return fail(LOVR_E_UNSUPPORTED, "gemm2: no instance for epi=%d act=%d", epi, act);
 }
 
-// 0 = 1-CTA kernel (cta_group::1), 1 = CTA-pair kernel (cta_group::2).  LOVR_GEMM_2CTA overrides the default.
+// Dense layers default to the CTA-pair kernel (cta_group::2; measured +6 % on qkv, +5 % on fc1/out-proj, +3.5 % on the
+// whole tower forward); LOVR_GEMM_2CTA=0 selects the 1-CTA kernel, which also serves M <= 128 and the batched score GEMMs.
 int gemm_use_pairs() {
   const char* e = getenv("LOVR_GEMM_2CTA");
-  return e ? atoi(e) : 0;
+  return e ? atoi(e) : 1;
 }
 
 // Dense layer: A [M,K] bf16 (lda), W [N,K] bf16 (ldw), C [M,N] (ldc; bf16 or fp32 by epilogue).
