@@ -15,6 +15,6 @@ echo "=== ncu launches"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 170 -c 400 --csv --log-file gpurun_out/launches.csv \
   python bench.py --steps 1 --warmup 1 --batch 128 --no-cpu-baseline --no-a-score > gpurun_out/ncu_launches.log 2>&1
 echo "=== ncu full"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'gemm_tcgen05|attention2_tcgen05|layernorm' -s 40 -c 8 -f -o gpurun_out/prof_gemm_attn \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'gemm2?_tcgen05|attention2_tcgen05|layernorm' -s 40 -c 10 -f -o gpurun_out/prof_gemm_attn \
   python bench.py --steps 1 --warmup 1 --batch 128 --no-cpu-baseline --no-a-score > gpurun_out/ncu_full.log 2>&1
 ls -la gpurun_out | tail -20
