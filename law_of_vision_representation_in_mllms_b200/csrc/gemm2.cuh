@@ -18,15 +18,17 @@ namespace lovr {
 
 // The residual epilogue trades one pipeline stage for a 4-deep staging ring per epilogue warp (two residual loads and two
 // stores in flight): it was the epilogue, not the main loop, that bounded the K=1024 out-projection.
-template <int EPI>
+// EW = epilogue warps: 4 (one per TMEM lane quarter, 256 columns each) or 8 (two per quarter, 128 columns each).
+template <int EPI, int EW>
 struct Gemm2Smem {
-  static constexpr int kStages = (EPI == EPI_RESID_F32) ? 5 : 6;
-  static constexpr int kResidBufs = (EPI == EPI_RESID_F32) ? 4 : 2;
+  static constexpr int kStages = (EPI == EPI_RESID_F32 || EW == 8) ? 5 : 6;
+  static constexpr int kResidBufs = (EPI == EPI_RESID_F32 && EW == 4) ? 4 : 2;
   static constexpr int kABytes = kBM * kBK * 2;        // 128 x 64 x 2
   static constexpr int kBBytes = 128 * kBK * 2;        // this CTA's half of the 256-row W tile
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagingBytes = kEpiWarps * kResidBufs * kStageBufBytes;
+  static constexpr int kStagingBytes = EW * kResidBufs * kStageBufBytes;
   static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + 512 + 1024;
+  static constexpr int kThreads = 64 + EW * 32;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -81,11 +83,12 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
       : "memory");
 }
 
-template <int EPI, int ACT, bool F16>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+template <int EPI, int ACT, bool F16, int EW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + EW * 32, 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmC, const GemmArgs p) {
-  using L = Gemm2Smem<EPI>;
+  using L = Gemm2Smem<EPI, EW>;
+  constexpr int CW = 256 / (EW / 4);  // columns per epilogue warp
   constexpr int kStages2 = L::kStages;
   constexpr int RB = L::kResidBufs;
   constexpr int BN = 256;
@@ -102,7 +105,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint64_t* tmem_full = bars + 2 * kStages2;       // [2]
   uint64_t* tmem_empty = bars + 2 * kStages2 + 2;  // [2]         (used in the leader)
   uint64_t* resid_bar = bars + 2 * kStages2 + 4;   // [kEpiWarps][RB]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages2 + 4 + RB * kEpiWarps);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages2 + 4 + RB * EW);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -125,9 +128,9 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 2 * kEpiWarps);
+      mbar_init(&tmem_empty[i], 2 * EW);
     }
-    for (int i = 0; i < RB * kEpiWarps; ++i) mbar_init(&resid_bar[i], 1);
+    for (int i = 0; i < RB * EW; ++i) mbar_init(&resid_bar[i], 1);
     fence_barrier_init();
   }
   cluster_sync_all();  // both CTAs' barriers exist before any remote signal
@@ -198,6 +201,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     // ===================================================================== epilogue warps (both CTAs)
     const int ew = warp - 2;
     const int quarter = warp & 3;
+    const int chalf = ew >> 2;  // which CW-column part of the tile this warp owns (always 0 when EW == 4)
     uint8_t* my_stage = staging + ew * RB * kStageBufBytes;
     uint64_t* my_rbar = resid_bar + ew * RB;
     const uint32_t row_sw = (lane & 7);
@@ -212,7 +216,8 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-      epilogue_tile<BN, EPI, ACT, F16, RB>(t_row, nt * BN, row0, 0, p, tmC, my_stage, my_rbar, lane, row_sw, g, run_max);
+      epilogue_tile<CW, EPI, ACT, F16, RB>(t_row + chalf * CW, nt * BN + chalf * CW, row0, 0, p, tmC, my_stage, my_rbar, lane,
+                                          row_sw, g, run_max);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[acc]), 0));  // leader's barrier

@@ -216,12 +216,12 @@ int launch_gemm(int bn, int epi, int act, bool f16, const CUtensorMap& a, const 
 
 constexpr int kDenseBN = 256;
 
-template <int EPI, int ACT, bool F16>
+template <int EPI, int ACT, bool F16, int EW>
 int launch_gemm2_inst(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const lovr::GemmArgs& args,
                       cudaStream_t s) {
-  auto kern = lovr::gemm2_tcgen05_kernel<EPI, ACT, F16>;
+  auto kern = lovr::gemm2_tcgen05_kernel<EPI, ACT, F16, EW>;
   static bool attr_set = false;
-  const int smem = lovr::Gemm2Smem<EPI>::kTotal;
+  const int smem = lovr::Gemm2Smem<EPI, EW>::kTotal;
   if (!attr_set) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
@@ -231,7 +231,7 @@ int launch_gemm2_inst(const CUtensorMap& a, const CUtensorMap& b, const CUtensor
   if (grid <= 0) return 0;
   size_t pidx = 0;
   const bool profiled = prof_begin(s, 2.0 * args.M * args.N * static_cast<double>(args.K), &pidx);
-  kern<<<grid, lovr::kGemmThreads, smem, s>>>(a, b, c, args);  // __cluster_dims__(2,1,1) on the kernel
+  kern<<<grid, lovr::Gemm2Smem<EPI, EW>::kThreads, smem, s>>>(a, b, c, args);  // __cluster_dims__(2,1,1) on the kernel
   if (profiled) prof_end(s, pidx);
   LAUNCH_CHECK("gemm2_tcgen05_kernel");
   return 0;
@@ -240,9 +240,18 @@ int launch_gemm2_inst(const CUtensorMap& a, const CUtensorMap& b, const CUtensor
 int launch_gemm2(int epi, int act, bool f16, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c,
                  const lovr::GemmArgs& args, cudaStream_t s) {
   using namespace lovr;
-#define LOVR_GEMM2_CASE(EPI_, ACT_)                                                                     \
-  if (epi == EPI_ && act == ACT_)                                                                       \
-    return f16 ? launch_gemm2_inst<EPI_, ACT_, true>(a, b, c, args, s) : launch_gemm2_inst<EPI_, ACT_, false>(a, b, c, args, s);
+  // epilogue warps: 8 (two per TMEM lane quarter) for the residual epilogue, whose per-chunk TMA round trip and proxy
+  // fence bound the K=1024 out-projection; LOVR_GEMM_EPI_WARPS=4|8 overrides for experiments
+  static const int ew_env = [] { const char* e = getenv("LOVR_GEMM_EPI_WARPS"); return e ? atoi(e) : 0; }();
+  const int ew = ew_env ? ew_env : (epi == EPI_RESID_F32 ? 8 : 4);
+#define LOVR_GEMM2_CASE(EPI_, ACT_)                                                                          \
+  if (epi == EPI_ && act == ACT_) {                                                                          \
+    if (ew == 8)                                                                                             \
+      return f16 ? launch_gemm2_inst<EPI_, ACT_, true, 8>(a, b, c, args, s)                                  \
+                 : launch_gemm2_inst<EPI_, ACT_, false, 8>(a, b, c, args, s);                                \
+    return f16 ? launch_gemm2_inst<EPI_, ACT_, true, 4>(a, b, c, args, s)                                    \
+               : launch_gemm2_inst<EPI_, ACT_, false, 4>(a, b, c, args, s);                                  \
+  }
   LOVR_GEMM2_CASE(EPI_BF16, ACT_NONE)
   LOVR_GEMM2_CASE(EPI_BF16, ACT_QUICK_GELU)
   LOVR_GEMM2_CASE(EPI_BF16, ACT_GELU_ERF)
