@@ -243,7 +243,7 @@ int launch_gemm2(int epi, int act, bool f16, const CUtensorMap& a, const CUtenso
   // epilogue warps: 8 (two per TMEM lane quarter) for the residual epilogue, whose per-chunk TMA round trip and proxy
   // fence bound the K=1024 out-projection; LOVR_GEMM_EPI_WARPS=4|8 overrides for experiments
   static const int ew_env = [] { const char* e = getenv("LOVR_GEMM_EPI_WARPS"); return e ? atoi(e) : 0; }();
-  const int ew = ew_env ? ew_env : (epi == EPI_RESID_F32 ? 8 : 4);
+  const int ew = ew_env ? ew_env : ((epi == EPI_RESID_F32 || act == ACT_GELU_ERF) ? 8 : 4);  // erf-GELU: +9 % with 8
 #define LOVR_GEMM2_CASE(EPI_, ACT_)                                                                          \
   if (epi == EPI_ && act == ACT_) {                                                                          \
     if (ew == 8)                                                                                             \
