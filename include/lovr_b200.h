@@ -157,6 +157,13 @@ int lovr_c_score_flow(const void* desc1, const void* desc2, int32_t dtype, int64
 int lovr_c_score_keypoints(const void* desc1, const void* desc2, int32_t dtype, int64_t n_pairs, int32_t P, int32_t D,
                            const int32_t* patch_idx, int32_t K, int32_t window, int32_t soft, float anno_size,
                            float* kps_out, void* workspace, size_t workspace_bytes, void* stream);
+/* Adaptive-flip test (C_score/utils/utils_correspondence.py:55-73 get_distance_mutual_nn; caller pck_train.py:111-126):
+ * out[b] = {mean over mutual nearest neighbours i <-> j of ||n(d1_i) - n(d2_j)||, number of mutual pairs}
+ * (NaN mean when there is none, like torch's mean of an empty selection).  Same dense similarity as lovr_c_score_flow;
+ * dist^2 = |n1|^2 + |n2|^2 - 2 n1.n2 (torch.cdist's matmul form). */
+size_t lovr_c_score_mutual_nn_workspace_bytes(int32_t dtype, int64_t n_pairs, int32_t P, int32_t D);
+int lovr_c_score_mutual_nn(const void* desc1, const void* desc2, int32_t dtype, int64_t n_pairs, int32_t P, int32_t D,
+                           float* out /* [n_pairs, 2] */, void* workspace, size_t workspace_bytes, void* stream);
 int lovr_pck(const float* pred, const float* gt, const uint8_t* visible, const float* thresholds, int64_t n_pairs,
              int32_t K, float* out, void* stream);
 
@@ -173,6 +180,39 @@ size_t lovr_cka_gram_elems(int32_t Dx, int32_t Dy);
 int lovr_cka_accumulate(const void* X, const void* Y, int64_t rows, int32_t Dx, int32_t Dy, double* gram,
                         void* workspace, size_t workspace_bytes, void* stream);
 int lovr_cka_finalize(const double* gram, double n_rows, int32_t Dx, int32_t Dy, double* out3, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Image preprocessing in front of the tower.  Replaces, bit for bit, the CPU path
+ *   llava/mm_utils.py:63-95  process_images / expand2square -> HF CLIPImageProcessor.preprocess
+ *                            (transformers 4.31 slow processor: PIL BICUBIC resize of the shortest edge, centre crop,
+ *                            float32(float64(v) * 1/255), (x - mean) / std in float32),
+ *   llava/model/multimodal_encoder/dinov2_encoder.py:24-26 (BitImageProcessor 256/224 and the 336x336 override),
+ *   SiglipImageProcessor (exact 224x224), and
+ *   C_score/extract_feature.py:65-67  img.resize((S,S)) [PIL default = BICUBIC] + (PILToTensor()(img)/255.0 - 0.5)*2.
+ * images: DEVICE buffer of n_img packed 8-bit RGB images (HWC, 3 bytes per pixel, rows contiguous);
+ * offsets_host[i] = byte offset of image i, hw_host[2*i], hw_host[2*i+1] = its height and width (HOST arrays: the
+ * library derives every per-image size from them and enqueues a small descriptor upload on `stream`).
+ * out [n_img, 3, crop_size, crop_size] in out_dtype (LOVR_DT_*).  Pillow's two-pass 8-bit resampling
+ * (libImaging/Resample.c; restated in oracle/preprocess_oracle.py) is integer arithmetic: results equal Pillow's.
+ * ------------------------------------------------------------------------------------------------- */
+enum { LOVR_RESIZE_SHORTEST_EDGE = 0, LOVR_RESIZE_EXACT = 1 };
+enum { LOVR_PIX_HF_RESCALE_NORMALIZE = 0, LOVR_PIX_CSCORE = 1 };
+typedef struct {
+  int32_t resize_mode;   /* LOVR_RESIZE_SHORTEST_EDGE: shortest edge -> resize_size, aspect kept (int(size*long/short));
+                            LOVR_RESIZE_EXACT: (resize_size, resize_size) */
+  int32_t resize_size;
+  int32_t crop_size;     /* centre crop (HF center_crop: top = (h - crop)//2); must be <= both resized sides */
+  int32_t pad_square;    /* 1: expand2square first (mm_utils.py:63-75, image_aspect_ratio == 'pad') */
+  uint8_t pad_rgb[4];    /* background colour of the square canvas: int(mean*255) per channel */
+  int32_t pixel_map;     /* LOVR_PIX_* : 8-bit value -> float */
+  float mean[3];
+  float std[3];
+} lovr_preprocess_config;
+
+size_t lovr_preprocess_workspace_bytes(const lovr_preprocess_config* cfg, int32_t n_img, const int32_t* hw_host);
+int lovr_preprocess(const uint8_t* images, const int64_t* offsets_host, const int32_t* hw_host, int32_t n_img,
+                    const lovr_preprocess_config* cfg, void* out, int32_t out_dtype, void* workspace,
+                    size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

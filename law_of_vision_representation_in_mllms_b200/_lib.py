@@ -14,6 +14,8 @@ DT_F32, DT_BF16, DT_F16 = 0, 1, 2
 EPI_BF16, EPI_RESID_F32, EPI_F32 = 0, 1, 2
 ATTN_TCGEN05, ATTN_SIMT_CHECK, ATTN_TCGEN05_V2, ATTN_TCGEN05_V2_PTMEM, ATTN_TCGEN05_V2_3PIPE = 0, 1, 2, 3, 4
 ATTN_AUTO = 5
+RESIZE_SHORTEST_EDGE, RESIZE_EXACT = 0, 1
+PIX_HF_RESCALE_NORMALIZE, PIX_CSCORE = 0, 1
 
 # every symbol include/lovr_b200.h declares (tests/test_abi.py checks the library exports all of them)
 EXPORTS = [
@@ -22,7 +24,9 @@ EXPORTS = [
     "lovr_gemm_bf16", "lovr_layernorm_bf16", "lovr_attention", "lovr_im2col",
     "lovr_a_score_workspace_bytes", "lovr_a_score_maxcos",
     "lovr_c_score_workspace_bytes", "lovr_c_score_flow", "lovr_c_score_keypoints", "lovr_pck",
+    "lovr_c_score_mutual_nn_workspace_bytes", "lovr_c_score_mutual_nn",
     "lovr_cka_workspace_bytes", "lovr_cka_gram_elems", "lovr_cka_accumulate", "lovr_cka_finalize",
+    "lovr_preprocess_workspace_bytes", "lovr_preprocess",
 ]
 
 
@@ -40,6 +44,12 @@ class LayerWeights(C.Structure):
 class TowerWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("patch_w", "patch_b", "cls", "pos", "pre_ln_w", "pre_ln_b")] + \
                [("layers_host", C.POINTER(LayerWeights))]
+
+
+class PreprocessConfig(C.Structure):
+    _fields_ = [("resize_mode", C.c_int32), ("resize_size", C.c_int32), ("crop_size", C.c_int32),
+                ("pad_square", C.c_int32), ("pad_rgb", C.c_uint8 * 4), ("pixel_map", C.c_int32),
+                ("mean", C.c_float * 3), ("std", C.c_float * 3)]
 
 
 class LovrError(RuntimeError):
@@ -93,6 +103,10 @@ def lib():
     L.lovr_c_score_flow.argtypes = [vp, vp, i32, i64, i32, i32, i32, i32, vp, vp, vp, sz, vp]
     L.lovr_c_score_keypoints.restype = C.c_int
     L.lovr_c_score_keypoints.argtypes = [vp, vp, i32, i64, i32, i32, vp, i32, i32, i32, f32, vp, vp, sz, vp]
+    L.lovr_c_score_mutual_nn_workspace_bytes.restype = sz
+    L.lovr_c_score_mutual_nn_workspace_bytes.argtypes = [i32, i64, i32, i32]
+    L.lovr_c_score_mutual_nn.restype = C.c_int
+    L.lovr_c_score_mutual_nn.argtypes = [vp, vp, i32, i64, i32, i32, vp, vp, sz, vp]
     L.lovr_pck.restype = C.c_int
     L.lovr_pck.argtypes = [vp, vp, vp, vp, i64, i32, vp, vp]
     L.lovr_cka_workspace_bytes.restype = sz
@@ -103,6 +117,11 @@ def lib():
     L.lovr_cka_accumulate.argtypes = [vp, vp, i64, i32, i32, vp, vp, sz, vp]
     L.lovr_cka_finalize.restype = C.c_int
     L.lovr_cka_finalize.argtypes = [vp, C.c_double, i32, i32, vp, vp]
+    L.lovr_preprocess_workspace_bytes.restype = sz
+    L.lovr_preprocess_workspace_bytes.argtypes = [C.POINTER(PreprocessConfig), i32, C.POINTER(C.c_int32)]
+    L.lovr_preprocess.restype = C.c_int
+    L.lovr_preprocess.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int32), i32, C.POINTER(PreprocessConfig), vp,
+                                  i32, vp, sz, vp]
     _lib = L
     return L
 

@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "liblovr_b200.so")
 SOURCES = ["lovr_b200.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared", "--use_fast_math=false"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", "-shared", "--use_fast_math=false"]
 
 
 def _newest_source_mtime():

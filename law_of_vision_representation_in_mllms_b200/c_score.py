@@ -157,3 +157,75 @@ def c_score(desc1, desc2, kps1, kps2, thresholds, categories, n_categories, soft
     vis = (kps1[..., 2] * kps2[..., 2]) > 0                      # pck_train.py:131
     pck = pck_per_pair(pred, kps2[..., :2], vis, thresholds)
     return category_sums(pck, categories, n_categories), pred
+
+
+# ---- adaptive flip (pck_train.py:111-126, ADAPT_FLIP + MUTUAL_NN) ---------------------------------------------------
+def get_distance_mutual_nn(desc1, desc2, return_count=False):
+    """== utils_correspondence.get_distance_mutual_nn(n(desc1), n(desc2)) per pair (:55-73): the mean descriptor distance
+    over mutually-nearest patch pairs.  desc [B,P*P,D] UN-normalised (normalisation fused) -> [B] fp32 (NaN where no mutual
+    pair exists, like torch's empty mean)."""
+    d1, d2, P = _prep(desc1, desc2, 64)
+    B, PP, D = d1.shape
+    L = _lib.lib()
+    dt = _lib.torch_dtype_code(d1.dtype)
+    out = torch.empty(B, 2, dtype=torch.float32, device=d1.device)
+    step = min(B, _DENSE_PAIRS_PER_CALL)
+    nbytes = L.lovr_c_score_mutual_nn_workspace_bytes(dt, step, P, D)
+    ws, base = _workspace(nbytes, d1.device)
+    with torch.cuda.device(d1.device):
+        st = _lib.stream_ptr(d1.device)
+        for s in range(0, B, step):
+            e = min(B, s + step)
+            _lib.check(L.lovr_c_score_mutual_nn(_lib.ptr(d1[s:e]), _lib.ptr(d2[s:e]), dt, e - s, P, D, _lib.ptr(out[s:e]),
+                                                base, nbytes, st), "lovr_c_score_mutual_nn")
+    return (out[:, 0], out[:, 1].long()) if return_count else out[:, 0]
+
+
+def permute_indices(flip_list, vis=None):
+    """utils/utils_geoware.py:151-189: index permutation that swaps left/right keypoint groups (`[4, 5]` -> 4<->5, longer
+    groups rotate); with `vis`, a group is only swapped when every member is visible."""
+    members = [g if isinstance(g, list) else [g] for g in flip_list]
+    perm = list(range(max(i for g in members for i in g) + 1))
+    for g in members:
+        if len(g) > 1 and (vis is None or all(bool(vis[i]) for i in g)):
+            for pos, i in enumerate(g):
+                perm[i] = g[(pos + 1) % len(g)]
+    return perm
+
+
+def flip_keypoints(keypoints, img_size, permute_list=None):
+    """utils/utils_geoware.py:199-204: mirror x, then reorder."""
+    out = keypoints.detach().clone()
+    out[:, 0] = img_size - out[:, 0]
+    return out if permute_list is None else out[permute_list]
+
+
+def optimized_kps_1_to_2(kps_1_to_2, kps_1_to_2_flip, img1_kps, img2_kps, flip_dist, original_dist, vis, permute_list,
+                         anno_size=ANNO_SIZE):
+    """utils/utils_geoware.py:269-280: if the mirrored source is closer to the target, take its predictions for the
+    keypoints that stay mutually visible after the flip."""
+    masked = img1_kps * vis.unsqueeze(-1).to(img1_kps.dtype)
+    flipped = flip_keypoints(masked, anno_size, permute_indices(permute_list, None))
+    vis_flip = (flipped[:, 2] * img2_kps[:, 2] * img1_kps[:, 2] > 0).to(kps_1_to_2.device)
+    if float(flip_dist) < float(original_dist):
+        kps_1_to_2 = kps_1_to_2.clone()
+        kps_1_to_2[vis_flip] = kps_1_to_2_flip[vis_flip]
+    return kps_1_to_2
+
+
+def keypoint_transformation_adaptive_flip(desc1, desc1_flip, desc2, kps1, kps2, permute_list, soft=True, window=5,
+                                          anno_size=ANNO_SIZE):
+    """pck_train.py:100-126 for ONE pair with ADAPT_FLIP and MUTUAL_NN: desc* [1,P*P,D] un-normalised, kps [K,3].
+    -> (kps_1_to_2 [K,2], original_dist, flip_dist).  Both keypoint transformations run as one batch of two pairs and
+    both distances as one batch of two dense similarities."""
+    P = int(round(desc1.shape[-2] ** 0.5))
+    k1, k2 = kps1.detach().cpu(), kps2.detach().cpu()
+    vis = k1[:, 2] * k2[:, 2] > 0
+    k1_flip = flip_keypoints(k1, anno_size, permute_indices(permute_list, vis))
+    idx = np.stack([kpts_to_patch_idx(k1, P, anno_size), kpts_to_patch_idx(k1_flip, P, anno_size)])
+    src = torch.cat([desc1.reshape(1, P * P, -1), desc1_flip.reshape(1, P * P, -1)])
+    tgt = desc2.reshape(1, P * P, -1).expand(2, -1, -1)
+    pred = keypoint_transformation(src, tgt, idx, soft, window, anno_size)
+    dist = get_distance_mutual_nn(src, tgt).cpu()
+    out = optimized_kps_1_to_2(pred[0], pred[1], k1, k2, dist[1], dist[0], vis, permute_list, anno_size)
+    return out, float(dist[0]), float(dist[1])

@@ -191,4 +191,110 @@ __global__ void pck_kernel(const float* __restrict__ pred, const float* __restri
   out[b * 4 + 3] = static_cast<float>(nv);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Mutual-nearest-neighbour distance of the adaptive-flip test (C_score/utils/utils_correspondence.py:55-73
+// get_distance_mutual_nn; caller pck_train.py:111-126).  The reference builds torch.cdist(n(d1), n(d2)) [P^2,P^2]; with
+// the cosine matrix sim = n(d1) n(d2)^T already produced by the tcgen05 GEMM, dist^2(i,j) = |n1_i|^2 + |n2_j|^2 - 2 sim(i,j)
+// (cdist's own matmul form), |n|^2 = (1 - 1e-10 * inv)^2 from the stored inv = 1 / (|d| + 1e-10).
+//   mnn_rows_kernel   warp per source row: min_j dist^2 and its first index
+//   mnn_cols_kernel   thread per target column: first index of min_i dist^2 (coalesced across the warp)
+//   mnn_reduce_kernel block per pair: mean over i with col_arg[row_arg[i]] == i of sqrt(max(dist^2, 0)); NaN when there is
+//                     no mutual pair (torch: mean of an empty tensor)
+__device__ __forceinline__ float unit_norm_sq(float inv) {
+  const float q = 1.0f - 1e-10f * inv;
+  return q * q;
+}
+
+__global__ void mnn_rows_kernel(const float* __restrict__ sim, size_t ld, const float* __restrict__ inv1,
+                                const float* __restrict__ inv2, int scale_ld, int PP, size_t rows,
+                                float* __restrict__ row_d2, int* __restrict__ row_arg) {
+  const int lane = threadIdx.x & 31;
+  const size_t row = blockIdx.x * static_cast<size_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const size_t b = row / PP;
+  const int i = static_cast<int>(row % PP);
+  const float* s = sim + row * ld;
+  const float* i2 = inv2 + b * scale_ld;
+  const float n1 = unit_norm_sq(__ldg(inv1 + b * scale_ld + i));
+  float bv = INFINITY;
+  int bi = 0x7fffffff;
+  for (int t = lane; t < PP; t += 32) {
+    const float v = n1 + unit_norm_sq(__ldg(i2 + t)) - 2.0f * __ldg(s + t);
+    if (v < bv) { bv = v; bi = t; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov < bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  if (lane == 0) {
+    row_d2[row] = bv;
+    row_arg[row] = bi;
+  }
+}
+
+// grid (ceil(PP / blockDim.x), row slabs, pairs): each thread scans one slab of rows of its column; slabs are merged
+// (first index on ties) by mnn_reduce_kernel.
+constexpr int kMnnSlabs = 8;
+__global__ void mnn_cols_kernel(const float* __restrict__ sim, size_t ld, const float* __restrict__ inv1,
+                                const float* __restrict__ inv2, int scale_ld, int PP, float* __restrict__ col_d2,
+                                int* __restrict__ col_arg) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int slab = blockIdx.y;
+  const size_t b = blockIdx.z;
+  if (j >= PP) return;
+  const int per = (PP + kMnnSlabs - 1) / kMnnSlabs;
+  const int i0 = slab * per, i1 = min(PP, i0 + per);
+  const float n2 = unit_norm_sq(__ldg(inv2 + b * scale_ld + j));
+  const float* s = sim + (b * PP) * ld + j;
+  const float* i1p = inv1 + b * scale_ld;
+  float bv = INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = i0; i < i1; ++i) {
+    const float v = unit_norm_sq(__ldg(i1p + i)) + n2 - 2.0f * __ldg(s + static_cast<size_t>(i) * ld);
+    if (v < bv) { bv = v; bi = i; }
+  }
+  const size_t o = (b * kMnnSlabs + slab) * PP + j;
+  col_d2[o] = bv;
+  col_arg[o] = bi;
+}
+
+__global__ void mnn_reduce_kernel(const float* __restrict__ row_d2, const int* __restrict__ row_arg,
+                                  const float* __restrict__ col_d2, const int* __restrict__ col_arg, int PP,
+                                  float* __restrict__ out) {
+  const size_t b = blockIdx.x;
+  __shared__ float s_sum[32];
+  __shared__ int s_cnt[32];
+  float sum = 0.f;
+  int cnt = 0;
+  for (int i = threadIdx.x; i < PP; i += blockDim.x) {
+    const int j = row_arg[b * PP + i];
+    float bv = INFINITY;
+    int bi = 0x7fffffff;
+    for (int sl = 0; sl < kMnnSlabs; ++sl) {  // slabs are in ascending row order: strict < keeps the first index
+      const size_t o = (b * kMnnSlabs + sl) * PP + j;
+      const float v = col_d2[o];
+      if (v < bv) { bv = v; bi = col_arg[o]; }
+    }
+    if (bi == i) {
+      sum += sqrtf(fmaxf(row_d2[b * PP + i], 0.f));
+      ++cnt;
+    }
+  }
+  sum = warp_sum(sum);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { s_sum[warp] = sum; s_cnt[warp] = cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    int c = 0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) { t += s_sum[w]; c += s_cnt[w]; }
+    out[b * 2 + 0] = t / static_cast<float>(c);  // 0/0 = NaN like torch's mean of an empty selection
+    out[b * 2 + 1] = static_cast<float>(c);
+  }
+}
+
 }  // namespace lovr

@@ -5,6 +5,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -21,6 +22,7 @@
 #include "cscore.cuh"
 #include "gemm.cuh"
 #include "gemm2.cuh"
+#include "preprocess.cuh"
 #include "rowwise.cuh"
 #include "scores.cuh"
 
@@ -855,19 +857,12 @@ size_t lovr_c_score_workspace_bytes(int32_t dtype, int64_t n_pairs, int32_t P, i
   return c_layout(dtype, n_pairs, P, D).total;
 }
 
-int lovr_c_score_flow(const void* desc1, const void* desc2, int32_t dtype, int64_t n_pairs, int32_t P, int32_t D,
-                      int32_t window, int32_t soft, float* flow, int32_t* argmax, void* workspace,
-                      size_t workspace_bytes, void* stream) {
+namespace {
+// n(desc1) n(desc2)^T for every pair into the workspace (layout l): inverse norms, optional fp32 -> 3 x bf16 split,
+// batched tcgen05 GEMM with row/column scales.  Shared by the dense flow and the mutual-NN distance.
+int c_dense_similarity(const void* desc1, const void* desc2, int32_t dtype, int64_t n_pairs, int32_t P, int32_t D,
+                       uint8_t* base, const CScoreLayout& l, cudaStream_t s) {
   using namespace lovr;
-  if (int rc = require_device()) return rc;
-  if (int rc = check_c_args(desc1, desc2, dtype, n_pairs, P, D)) return rc;
-  if (!flow || !workspace) return fail(LOVR_E_ARG, "c_score_flow: null pointer");
-  if (D % 64) return fail(LOVR_E_ARG, "c_score_flow: D=%d must be a multiple of 64 (pad channels with zeros)", D);
-  const CScoreLayout l = c_layout(dtype, n_pairs, P, D);
-  if (workspace_bytes < l.total) return fail(LOVR_E_NOMEM, "c_score workspace %zu < %zu", workspace_bytes, l.total);
-  if (reinterpret_cast<uintptr_t>(workspace) & 1023) return fail(LOVR_E_ARG, "workspace must be 1024-byte aligned");
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  auto base = static_cast<uint8_t*>(workspace);
   float* inv1 = reinterpret_cast<float*>(base + l.inv1);
   float* inv2 = reinterpret_cast<float*>(base + l.inv2);
   float* sim = reinterpret_cast<float*>(base + l.sim);
@@ -905,8 +900,78 @@ int lovr_c_score_flow(const void* desc1, const void* desc2, int32_t dtype, int64
   GemmArgs g{};
   g.M = PP; g.N = PP; g.K = K; g.batch = static_cast<int>(n_pairs); g.n_inner = 1;
   g.bias = nullptr; g.colscale = inv2; g.rowscale = inv1; g.rowmax = nullptr; g.n_valid = PP; g.scale_ld = l.scale_ld;
-  if ((rc = launch_gemm(256, EPI_F32, ACT_NONE, false, ta, tb, tc, g, s))) return rc;
-  return launch_flow_rows(sim, l.sim_ld, rows, P, window, soft, 0.f, flow, argmax, s);
+  return launch_gemm(256, EPI_F32, ACT_NONE, false, ta, tb, tc, g, s);
+}
+struct MnnLayout {
+  size_t row_d2, row_arg, col_d2, col_arg, total;
+};
+MnnLayout mnn_layout(const CScoreLayout& l, int64_t n, int P) {
+  MnnLayout m{};
+  const size_t PP = static_cast<size_t>(P) * P;
+  size_t off = l.total;
+  m.row_d2 = off; off += align_up(static_cast<size_t>(n) * PP * 4, 1024);
+  m.row_arg = off; off += align_up(static_cast<size_t>(n) * PP * 4, 1024);
+  m.col_d2 = off; off += align_up(static_cast<size_t>(n) * lovr::kMnnSlabs * PP * 4, 1024);
+  m.col_arg = off; off += align_up(static_cast<size_t>(n) * lovr::kMnnSlabs * PP * 4, 1024);
+  m.total = off;
+  return m;
+}
+}  // namespace
+
+int lovr_c_score_flow(const void* desc1, const void* desc2, int32_t dtype, int64_t n_pairs, int32_t P, int32_t D,
+                      int32_t window, int32_t soft, float* flow, int32_t* argmax, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  if (int rc = require_device()) return rc;
+  if (int rc = check_c_args(desc1, desc2, dtype, n_pairs, P, D)) return rc;
+  if (!flow || !workspace) return fail(LOVR_E_ARG, "c_score_flow: null pointer");
+  if (D % 64) return fail(LOVR_E_ARG, "c_score_flow: D=%d must be a multiple of 64 (pad channels with zeros)", D);
+  const CScoreLayout l = c_layout(dtype, n_pairs, P, D);
+  if (workspace_bytes < l.total) return fail(LOVR_E_NOMEM, "c_score workspace %zu < %zu", workspace_bytes, l.total);
+  if (reinterpret_cast<uintptr_t>(workspace) & 1023) return fail(LOVR_E_ARG, "workspace must be 1024-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  auto base = static_cast<uint8_t*>(workspace);
+  if (int rc = c_dense_similarity(desc1, desc2, dtype, n_pairs, P, D, base, l, s)) return rc;
+  return launch_flow_rows(reinterpret_cast<float*>(base + l.sim), l.sim_ld, static_cast<size_t>(n_pairs) * P * P, P,
+                          window, soft, 0.f, flow, argmax, s);
+}
+
+size_t lovr_c_score_mutual_nn_workspace_bytes(int32_t dtype, int64_t n_pairs, int32_t P, int32_t D) {
+  return mnn_layout(c_layout(dtype, n_pairs, P, D), n_pairs, P).total;
+}
+
+int lovr_c_score_mutual_nn(const void* desc1, const void* desc2, int32_t dtype, int64_t n_pairs, int32_t P, int32_t D,
+                           float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace lovr;
+  if (int rc = require_device()) return rc;
+  if (int rc = check_c_args(desc1, desc2, dtype, n_pairs, P, D)) return rc;
+  if (!out || !workspace) return fail(LOVR_E_ARG, "c_score_mutual_nn: null pointer");
+  if (D % 64) return fail(LOVR_E_ARG, "c_score_mutual_nn: D=%d must be a multiple of 64 (pad channels with zeros)", D);
+  if (n_pairs > 65535) return fail(LOVR_E_ARG, "c_score_mutual_nn: at most 65535 pairs per call");
+  const CScoreLayout l = c_layout(dtype, n_pairs, P, D);
+  const MnnLayout m = mnn_layout(l, n_pairs, P);
+  if (workspace_bytes < m.total) return fail(LOVR_E_NOMEM, "c_score_mutual_nn workspace %zu < %zu", workspace_bytes, m.total);
+  if (reinterpret_cast<uintptr_t>(workspace) & 1023) return fail(LOVR_E_ARG, "workspace must be 1024-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  auto base = static_cast<uint8_t*>(workspace);
+  if (int rc = c_dense_similarity(desc1, desc2, dtype, n_pairs, P, D, base, l, s)) return rc;
+  const float* sim = reinterpret_cast<const float*>(base + l.sim);
+  const float* inv1 = reinterpret_cast<const float*>(base + l.inv1);
+  const float* inv2 = reinterpret_cast<const float*>(base + l.inv2);
+  float* row_d2 = reinterpret_cast<float*>(base + m.row_d2);
+  int* row_arg = reinterpret_cast<int*>(base + m.row_arg);
+  float* col_d2 = reinterpret_cast<float*>(base + m.col_d2);
+  int* col_arg = reinterpret_cast<int*>(base + m.col_arg);
+  const int PP = P * P;
+  const size_t rows = static_cast<size_t>(n_pairs) * PP;
+  mnn_rows_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, s>>>(sim, l.sim_ld, inv1, inv2, l.scale_ld, PP, rows,
+                                                                        row_d2, row_arg);
+  LAUNCH_CHECK("mnn_rows_kernel");
+  mnn_cols_kernel<<<dim3((PP + 127) / 128, kMnnSlabs, static_cast<unsigned>(n_pairs)), 128, 0, s>>>(
+      sim, l.sim_ld, inv1, inv2, l.scale_ld, PP, col_d2, col_arg);
+  LAUNCH_CHECK("mnn_cols_kernel");
+  mnn_reduce_kernel<<<static_cast<unsigned>(n_pairs), 256, 0, s>>>(row_d2, row_arg, col_d2, col_arg, PP, out);
+  LAUNCH_CHECK("mnn_reduce_kernel");
+  return 0;
 }
 
 int lovr_c_score_keypoints(const void* desc1, const void* desc2, int32_t dtype, int64_t n_pairs, int32_t P, int32_t D,
@@ -1043,6 +1108,132 @@ int lovr_cka_finalize(const double* gram, double n_rows, int32_t Dx, int32_t Dy,
   const size_t na = static_cast<size_t>(Dx) * (Dx + Dy), nb = static_cast<size_t>(Dy) * Dy;
   lovr::cka_finalize_kernel<<<296, 256, 0, s>>>(gram, gram + na, gram + na + nb, n_rows, Dx, Dy, out3);
   LAUNCH_CHECK("cka_finalize_kernel");
+  return 0;
+}
+
+// ====================================================================================== image preprocessing
+namespace {
+struct PrePlan {
+  std::vector<lovr::PreImg> imgs;
+  size_t coef_off = 0, tmp_off = 0, total = 0;
+  int max_rows = 0;
+};
+// Resample.c precompute_coeffs bounds of output xx (same double operations as resample_coeffs_kernel; this file is
+// compiled with -ffp-contract=off so the host never fuses them)
+void resample_bounds(int in_size, int out_size, int xx, int* xmin, int* xmax, int* ksize) {
+  const double scale = static_cast<double>(in_size) / static_cast<double>(out_size);
+  const double filterscale = scale < 1.0 ? 1.0 : scale;
+  const double support = 2.0 * filterscale;
+  const double center = (static_cast<double>(xx) + 0.5) * scale;
+  int lo = static_cast<int>(center - support + 0.5);
+  if (lo < 0) lo = 0;
+  int hi = static_cast<int>(center + support + 0.5);
+  if (hi > in_size) hi = in_size;
+  *xmin = lo;
+  *xmax = hi;
+  *ksize = static_cast<int>(ceil(support)) * 2 + 1;
+}
+int pre_plan(const lovr_preprocess_config* cfg, int32_t n_img, const int32_t* hw, const int64_t* offsets, PrePlan* plan) {
+  if (!cfg || !hw || n_img <= 0 || n_img > 65535)
+    return fail(LOVR_E_ARG, "preprocess: null config / sizes, or n_img outside [1, 65535]");
+  const int R = cfg->crop_size, S = cfg->resize_size;
+  if (R <= 0 || S <= 0 || S < R) return fail(LOVR_E_ARG, "preprocess: need 0 < crop_size <= resize_size (got %d, %d)", R, S);
+  if (cfg->resize_mode != LOVR_RESIZE_SHORTEST_EDGE && cfg->resize_mode != LOVR_RESIZE_EXACT)
+    return fail(LOVR_E_ARG, "preprocess: unknown resize_mode %d", cfg->resize_mode);
+  if (cfg->pixel_map != LOVR_PIX_HF_RESCALE_NORMALIZE && cfg->pixel_map != LOVR_PIX_CSCORE)
+    return fail(LOVR_E_ARG, "preprocess: unknown pixel_map %d", cfg->pixel_map);
+  plan->imgs.resize(n_img);
+  size_t coef_ints = 0, tmp_bytes = 0;
+  for (int i = 0; i < n_img; ++i) {
+    lovr::PreImg& im = plan->imgs[i];
+    im.H = hw[2 * i];
+    im.W = hw[2 * i + 1];
+    if (im.H <= 0 || im.W <= 0 || im.H > 32768 || im.W > 32768)
+      return fail(LOVR_E_ARG, "preprocess: image %d has unsupported size %dx%d", i, im.H, im.W);
+    im.src_off = offsets ? offsets[i] : 0;
+    im.vH = im.H;
+    im.vW = im.W;
+    im.pad_top = im.pad_left = 0;
+    if (cfg->pad_square && im.H != im.W) {  // mm_utils.py:63-75: paste at ((side - w)//2, 0) or (0, (side - h)//2)
+      const int side = im.H > im.W ? im.H : im.W;
+      im.pad_top = (side - im.H) / 2;
+      im.pad_left = (side - im.W) / 2;
+      im.vH = im.vW = side;
+    }
+    if (cfg->resize_mode == LOVR_RESIZE_EXACT) {
+      im.newH = im.newW = S;
+    } else {  // transformers get_resize_output_image_size(default_to_square=False)
+      const int shrt = im.vW <= im.vH ? im.vW : im.vH, lng = im.vW <= im.vH ? im.vH : im.vW;
+      const int new_long = static_cast<int>(static_cast<double>(static_cast<long long>(S) * lng) / shrt);
+      im.newH = im.vW <= im.vH ? new_long : S;
+      im.newW = im.vW <= im.vH ? S : new_long;
+    }
+    if (im.newH < R || im.newW < R)
+      return fail(LOVR_E_ARG, "preprocess: image %d resizes to %dx%d, smaller than the crop %d (zero-padding crop is not on this path)",
+                  i, im.newH, im.newW, R);
+    im.crop_top = (im.newH - R) / 2;
+    im.crop_left = (im.newW - R) / 2;
+    int lo, hi, k, lo2, hi2;
+    resample_bounds(im.vW, im.newW, im.crop_left, &lo, &hi, &k);
+    im.kx = k;
+    resample_bounds(im.vH, im.newH, im.crop_top, &lo, &hi, &k);
+    resample_bounds(im.vH, im.newH, im.crop_top + R - 1, &lo2, &hi2, &k);
+    im.ky = k;
+    im.row0 = lo;
+    im.rows = hi2 - lo;
+    im.coef_off = static_cast<long long>(coef_ints);
+    im.tmp_off = static_cast<long long>(tmp_bytes);
+    coef_ints += static_cast<size_t>(R) * (2 + im.kx) + static_cast<size_t>(R) * (2 + im.ky);
+    tmp_bytes += align_up(static_cast<size_t>(3) * im.rows * R, 16);
+    if (im.rows > plan->max_rows) plan->max_rows = im.rows;
+  }
+  plan->coef_off = align_up(static_cast<size_t>(n_img) * sizeof(lovr::PreImg), 256);
+  plan->tmp_off = plan->coef_off + align_up(coef_ints * 4, 256);
+  plan->total = plan->tmp_off + align_up(tmp_bytes, 256);
+  return 0;
+}
+}  // namespace
+
+size_t lovr_preprocess_workspace_bytes(const lovr_preprocess_config* cfg, int32_t n_img, const int32_t* hw_host) {
+  PrePlan plan;
+  if (pre_plan(cfg, n_img, hw_host, nullptr, &plan)) return 0;
+  return plan.total;
+}
+
+int lovr_preprocess(const uint8_t* images, const int64_t* offsets_host, const int32_t* hw_host, int32_t n_img,
+                    const lovr_preprocess_config* cfg, void* out, int32_t out_dtype, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+  if (int rc = require_device()) return rc;
+  if (n_img == 0) return 0;
+  if (!images || !offsets_host || !out || !workspace) return fail(LOVR_E_ARG, "preprocess: null pointer");
+  if (out_dtype != LOVR_DT_F32 && out_dtype != LOVR_DT_BF16 && out_dtype != LOVR_DT_F16)
+    return fail(LOVR_E_ARG, "preprocess: unsupported out_dtype %d", out_dtype);
+  PrePlan plan;
+  if (int rc = pre_plan(cfg, n_img, hw_host, offsets_host, &plan)) return rc;
+  if (workspace_bytes < plan.total)
+    return fail(LOVR_E_NOMEM, "preprocess: workspace %zu < required %zu bytes", workspace_bytes, plan.total);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  const lovr::PreImg* d_imgs = reinterpret_cast<const lovr::PreImg*>(ws);
+  int* d_coefs = reinterpret_cast<int*>(ws + plan.coef_off);
+  uint8_t* d_tmp = ws + plan.tmp_off;
+  // pageable source: the runtime stages the descriptors before returning, so `plan` may die at scope exit
+  CUDA_TRY(cudaMemcpyAsync(ws, plan.imgs.data(), plan.imgs.size() * sizeof(lovr::PreImg), cudaMemcpyHostToDevice, s));
+  const int R = cfg->crop_size;
+  lovr::resample_coeffs_kernel<<<dim3((R + 127) / 128, 2, n_img), 128, 0, s>>>(d_imgs, d_coefs, n_img, R);
+  LAUNCH_CHECK("resample_coeffs_kernel");
+  const uint32_t bg = cfg->pad_rgb[0] | (cfg->pad_rgb[1] << 8) | (cfg->pad_rgb[2] << 16);
+  lovr::resample_h_kernel<<<dim3((plan.max_rows + lovr::kPreRowsPerBlock - 1) / lovr::kPreRowsPerBlock, n_img), 256, 0, s>>>(
+      images, d_imgs, d_coefs, d_tmp, R, bg);
+  LAUNCH_CHECK("resample_h_kernel");
+  lovr::PixelMap pm;
+  pm.mode = cfg->pixel_map;
+  for (int c = 0; c < 3; ++c) {
+    pm.mean[c] = cfg->mean[c];
+    pm.stdv[c] = cfg->std[c];
+  }
+  lovr::resample_v_kernel<<<dim3(R, n_img), 256, 0, s>>>(d_tmp, d_imgs, d_coefs, out, out_dtype, R, pm);
+  LAUNCH_CHECK("resample_v_kernel");
   return 0;
 }
 

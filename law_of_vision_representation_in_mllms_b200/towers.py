@@ -176,7 +176,10 @@ class _B200VisionTower(nn.Module):
         return inst
 
     def _make_image_processor(self):
-        return None
+        """Reference: `CLIPImageProcessor.from_pretrained` (clip_encoder.py:23) / `AutoImageProcessor` (dinov2_encoder.py:24,
+        siglip_encoder.py:24).  Here: the GPU processor with the checkpoint's preprocessor_config values."""
+        from .preprocess import processor_for
+        return processor_for(self.vision_tower_name, self._default_image_size(), self._device)
 
     # ---- forward --------------------------------------------------------------------------------
     def _select(self):

@@ -85,3 +85,49 @@ def pck_per_image(pred, gt, vis, thr, alphas=(0.1, 0.05, 0.01)):
 def weighted_pck(per_category_means, weights):
     """C_score/utils/logger.py:61-65 — np.average over categories weighted by #pairs."""
     return float(np.average(per_category_means, weights=weights))
+
+
+# ---- adaptive flip (pck_train.py:111-126) ------------------------------------------------------------------------
+def mutual_nn_distance(desc1, desc2):
+    """utils_correspondence.py:55-73 get_distance_mutual_nn on normalised descriptors [1,P*P,C], restated in fp64
+    (direct differences; the reference's torch.cdist takes the fp32 matmul form for P*P > 25).
+    -> (mean distance over mutual nearest neighbours, their count)."""
+    a, b = desc1[0].double(), desc2[0].double()
+    d = torch.cdist(a, b, compute_mode="donot_use_mm_for_euclid_dist")
+    nn12 = d.argmin(dim=1)
+    nn21 = d.argmin(dim=0)
+    mutual = nn21[nn12] == torch.arange(d.shape[0])
+    return float(d.min(dim=1).values[mutual].mean()), int(mutual.sum())
+
+
+def permute_indices(flip_list, vis=None):
+    """utils/utils_geoware.py:151-189 — left/right keypoint swaps; a group is swapped only if all its members are visible."""
+    flat = [i for item in flip_list for i in (item if isinstance(item, list) else [item])]
+    indices = list(range(max(flat) + 1))
+    for item in flip_list:
+        if isinstance(item, list) and (vis is None or all(vis[i] for i in item)):
+            for i in range(len(item)):
+                indices[item[i]] = item[(i + 1) % len(item)]
+    return indices
+
+
+def flip_keypoints(kps, img_size, permute_list=None):
+    """utils/utils_geoware.py:199-204."""
+    out = kps.detach().clone()
+    out[:, 0] = img_size - out[:, 0]
+    if permute_list is not None:
+        out = out[permute_list]
+    return out
+
+
+def optimized_kps_1_to_2(kps_1_to_2, kps_1_to_2_flip, img1_kps, img2_kps, flip_dist, original_dist, vis, permute_list,
+                         anno_size=ANNO_SIZE):
+    """utils/utils_geoware.py:269-280 — take the flipped prediction for the keypoints that stay mutually visible after
+    the flip when the flipped source is closer (mutual-NN distance) to the target."""
+    mutual = img1_kps * vis.unsqueeze(-1).float()
+    flipped = flip_keypoints(mutual, anno_size, permute_indices(permute_list, None))
+    vis_flip = flipped[:, 2] * img2_kps[:, 2] * img1_kps[:, 2] > 0
+    out = kps_1_to_2.clone()
+    if flip_dist < original_dist:
+        out[vis_flip] = kps_1_to_2_flip[vis_flip]
+    return out

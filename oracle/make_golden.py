@@ -1,7 +1,7 @@
 """Generate tests/golden/*.pt by running the REFERENCE's own code (from /root/reference, read-only)
 on seeded synthetic inputs.  Run in the build container only (the GPU box has no /root/reference):
 
-    python oracle/make_golden.py [vit] [ascore] [cscore]
+    python oracle/make_golden.py [vit] [ascore] [cscore] [preprocess] [flip]
 
 What runs from the reference, unmodified:
   * llava/model/multimodal_encoder/{clip,dinov2,siglip}_encoder.py — loaded by file path; only the
@@ -9,6 +9,10 @@ What runs from the reference, unmodified:
     that build the HF model from a config and load our seeded synthetic state dict.
   * A_score/compute.py — exec'd with only its two hard-coded path/list lines (:7, :10) substituted.
   * C_score/utils/utils_correspondence.py — imported by file path.
+  * llava/mm_utils.py (process_images, expand2square) — loaded by file path with a stub `llava` package holding the
+    reference's own llava/constants.py; driven with transformers' PIL-backend processors (the descendants of the 4.31 slow
+    processors the reference pins) and Pillow itself; the three C-score lines of C_score/extract_feature.py:65-67 are
+    executed verbatim (the script itself needs a GPU and checkpoints).
 Inputs are regenerated from seeds by tests (law_of_vision_representation_in_mllms_b200.weights /
 oracle.synth), so fixtures hold only outputs.
 """
@@ -218,10 +222,101 @@ def make_cscore():
     torch.save(out, os.path.join(GOLD, "c_score.pt"))
 
 
+# ----------------------------------------------------------------------------------- adaptive flip
+def make_flip():
+    """The reference's pck_train.py:103-126 block (ADAPT_FLIP + MUTUAL_NN) driven with its own functions:
+    utils_correspondence.{kpts_to_patch_idx, calculate_keypoint_transformation, get_distance_mutual_nn} and
+    utils_geoware.{permute_indices, flip_keypoints, optimized_kps_1_to_2}.  Those call `.cuda()` on their tensors:
+    here (no GPU) `Tensor.cuda` is made the identity for the duration of the run."""
+    uc = _load(os.path.join(REF, "C_score/utils/utils_correspondence.py"), "ref_utils_correspondence")
+    ug = _load(os.path.join(REF, "C_score/utils/utils_geoware.py"), "ref_utils_geoware")
+    nf = lambda f: f / (torch.linalg.norm(f, dim=-1)[:, :, None] + 1e-10)      # pck_train.py:24-29
+    real_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    out = {}
+    try:
+        for cname, cfg in synth.FLIP_CASES.items():
+            d1, d1f, d2, kps1, kps2 = synth.flip_case(cfg)
+            P = cfg["P"]
+            args = types.SimpleNamespace(ANNO_SIZE=840, SOFT_EVAL=True, SOFT_EVAL_WINDOW=5)
+            img1_desc, img1_desc_flip, img2_desc = nf(d1), nf(d1f), nf(d2)
+            vis = kps1[:, 2] * kps2[:, 2] > 0                                                        # :100
+            idx = uc.kpts_to_patch_idx(args, kps1, P)                                                # :106
+            kps_1_to_2 = uc.calculate_keypoint_transformation(args, img1_desc, img2_desc, torch.as_tensor(idx).long(), P)
+            permute_list = cfg["permute"]
+            kps1_flip = ug.flip_keypoints(kps1, args.ANNO_SIZE, ug.permute_indices(permute_list, vis))   # :114
+            idx_flip = uc.kpts_to_patch_idx(args, kps1_flip, P)                                      # :115
+            kps_1_to_2_flip = uc.calculate_keypoint_transformation(args, img1_desc_flip, img2_desc,
+                                                                   torch.as_tensor(idx_flip).long(), P)
+            original_dist = uc.get_distance_mutual_nn(img1_desc, img2_desc)                          # :120
+            flip_dist = uc.get_distance_mutual_nn(img1_desc_flip, img2_desc)                         # :121
+            final = ug.optimized_kps_1_to_2(args, kps_1_to_2.clone(), kps_1_to_2_flip, kps1, kps2, flip_dist,
+                                            original_dist, vis, permute_list)                         # :126
+            out[cname] = dict(original_dist=float(original_dist), flip_dist=float(flip_dist), kps=kps_1_to_2.clone(),
+                              kps_flip=kps_1_to_2_flip.clone(), final=final.clone(), idx_flip=torch.as_tensor(idx_flip),
+                              kps1_flip=kps1_flip.clone())
+            print("flip", cname, out[cname]["original_dist"], out[cname]["flip_dist"])
+    finally:
+        torch.Tensor.cuda = real_cuda
+    torch.save(out, os.path.join(GOLD, "c_score_flip.pt"))
+
+
+# ----------------------------------------------------------------------------------- preprocessing
+def make_preprocess():
+    """Outputs are bit-exact quantities: the fixture stores their SHA-256 (+ shape and a few samples), not the tensors."""
+    import hashlib
+    from PIL import Image
+    from torchvision.transforms import PILToTensor
+    from transformers.models.bit.image_processing_pil_bit import BitImageProcessorPil
+    from transformers.models.clip.image_processing_pil_clip import CLIPImageProcessorPil
+    from transformers.models.siglip.image_processing_pil_siglip import SiglipImageProcessorPil
+    pkg = types.ModuleType("llava")
+    pkg.__path__ = []
+    sys.modules["llava"] = pkg
+    sys.modules["llava.constants"] = _load(os.path.join(REF, "llava/constants.py"), "llava.constants")
+    mm = _load(os.path.join(REF, "llava/mm_utils.py"), "ref_mm_utils")
+    imgs = [Image.fromarray(a) for a in synth.preprocess_images()]
+    out = {}
+    for cname, cfg in synth.PREPROCESS_CASES.items():
+        sel = [imgs[i] for i in cfg["images"]]
+        if cfg["kind"] == "cscore":
+            res = []
+            for img in sel:
+                img_size = cfg["size"]
+                img = img.convert('RGB')                                   # extract_feature.py:65
+                img = img.resize((img_size, img_size))                     # :66
+                img_tensor = (PILToTensor()(img) / 255.0 - 0.5) * 2        # :67
+                res.append(img_tensor)
+            t = torch.stack(res)
+        else:
+            mean, std = synth.PREPROCESS_NORMS[cfg["norm"]]
+            size = {"height": cfg["size"], "width": cfg["size"]} if cfg["exact"] else {"shortest_edge": cfg["size"]}
+            crop = {"height": cfg["crop"], "width": cfg["crop"]}
+            cls = {"clip": CLIPImageProcessorPil, "imagenet": BitImageProcessorPil, "half": SiglipImageProcessorPil}[cfg["norm"]]
+            kw = dict(size=size, image_mean=mean, image_std=std, resample=3)
+            if cls is not SiglipImageProcessorPil:
+                kw["crop_size"] = crop
+            proc = cls(**kw)
+            mcfg = types.SimpleNamespace(image_aspect_ratio="pad" if cfg.get("pad") else None)
+            t = mm.process_images(sel, proc, mcfg)                         # the reference's own function
+            t = torch.as_tensor(t)
+            if t.dim() == 3:
+                t = t[None]
+        t = t.contiguous().float()
+        out[cname] = dict(shape=tuple(t.shape), sha256=hashlib.sha256(t.numpy().tobytes()).hexdigest(),
+                          sample=t[0, :, ::37, ::41].clone())
+        print("preprocess", cname, out[cname]["shape"], out[cname]["sha256"][:16])
+    torch.save(out, os.path.join(GOLD, "preprocess.pt"))
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
-    what = sys.argv[1:] or ["vit", "ascore", "cscore"]
+    what = sys.argv[1:] or ["vit", "ascore", "cscore", "preprocess", "flip"]
     torch.set_num_threads(os.cpu_count())
+    if "preprocess" in what:
+        make_preprocess()
+    if "flip" in what:
+        make_flip()
     if "ascore" in what:
         make_ascore()
     if "cscore" in what:

@@ -68,3 +68,74 @@ def c_score_pair(cfg):
     kps = torch.rand(K, 3, generator=g) * 839.0
     kps[:, 2] = 1.0
     return d1, d2, kps
+
+
+# ---- image preprocessing: seeded 8-bit RGB images (smooth structure + texture + noise, so resampling is non-trivial)
+PREPROCESS_IMAGE_SIZES = [(480, 640), (500, 333), (224, 224), (336, 500), (97, 61), (700, 1000)]   # (H, W)
+
+# processor configurations as the checkpoints' preprocessor_config.json state them (size, crop, mean/std family, exact)
+PREPROCESS_CASES = {
+    "clip336": dict(kind="hf", size=336, crop=336, norm="clip", exact=False, images=[0]),
+    "clip336_pad": dict(kind="hf", size=336, crop=336, norm="clip", exact=False, pad=True, images=[0, 1, 2, 4]),
+    "clip224": dict(kind="hf", size=224, crop=224, norm="clip", exact=False, images=[1]),
+    "clip224_upscale": dict(kind="hf", size=224, crop=224, norm="clip", exact=False, images=[4]),
+    "dinov2_256_224": dict(kind="hf", size=256, crop=224, norm="imagenet", exact=False, images=[3]),
+    "dinov2_336_override": dict(kind="hf", size=336, crop=336, norm="imagenet", exact=True, images=[0]),
+    "siglip224": dict(kind="hf", size=224, crop=224, norm="half", exact=True, images=[5]),
+    "cscore224": dict(kind="cscore", size=224, images=[0]),
+    "cscore224_b": dict(kind="cscore", size=224, images=[5]),
+}
+PREPROCESS_NORMS = {
+    "clip": ([0.48145466, 0.4578275, 0.40821073], [0.26862954, 0.26130258, 0.27577711]),
+    "imagenet": ([0.485, 0.456, 0.406], [0.229, 0.224, 0.225]),
+    "half": ([0.5, 0.5, 0.5], [0.5, 0.5, 0.5]),
+}
+
+
+def synthetic_rgb_image(h, w, seed):
+    """-> HWC uint8 numpy array."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float64)
+    img = np.empty((h, w, 3), np.float64)
+    for c in range(3):
+        fx, fy, ph = rng.uniform(0.01, 0.3), rng.uniform(0.01, 0.3), rng.uniform(0, 6.28)
+        img[..., c] = 127 + 90 * np.sin(fx * xx + fy * yy + ph) + 40 * np.sign(np.sin(0.11 * (c + 1) * xx) * np.sin(0.07 * yy))
+    img += rng.normal(0, 12, img.shape)
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+def preprocess_images():
+    return [synthetic_rgb_image(h, w, 4000 + i) for i, (h, w) in enumerate(PREPROCESS_IMAGE_SIZES)]
+
+
+# ---- adaptive flip: (desc1, desc1 of the mirrored image, desc2, keypoints with left/right groups) per case
+FLIP_CASES = {
+    # desc2 is built from the MIRRORED source -> the flipped descriptors are closer: predictions of swapped groups are taken
+    "p16_flip_wins": dict(seed=31, P=16, D=256, K=10, corr=0.7, from_flip=True,
+                          permute=[0, [1, 2], 3, [4, 5], [6, 7, 8, 9]], invisible=(7,)),
+    "p16_orig_wins": dict(seed=32, P=16, D=256, K=10, corr=0.7, from_flip=False,
+                          permute=[0, [1, 2], 3, [4, 5], [6, 7, 8, 9]], invisible=()),
+    "p24_flip_wins": dict(seed=33, P=24, D=1024, K=8, corr=0.5, from_flip=True,
+                          permute=[[0, 1], [2, 3], 4, 5, [6, 7]], invisible=(2,)),
+}
+
+
+def flip_case(cfg):
+    """-> desc1, desc1_flip, desc2 [1,P*P,D] un-normalised fp32; kps1, kps2 [K,3] (x, y, visible)."""
+    g = torch.Generator().manual_seed(cfg["seed"])
+    P, D, K = cfg["P"], cfg["D"], cfg["K"]
+    grid = torch.randn(P, P, D, generator=g)
+    d1 = grid.reshape(1, P * P, D)
+    # the mirrored image's features: mirrored grid plus a perturbation (a tower is not exactly flip-equivariant)
+    d1f = (torch.flip(grid, dims=(1,)) + 0.3 * torch.randn(P, P, D, generator=g)).reshape(1, P * P, D)
+    src = d1f if cfg["from_flip"] else d1
+    d2 = cfg["corr"] * src + (1 - cfg["corr"]) * torch.randn(1, P * P, D, generator=g)
+    d1 = d1 * (0.5 + torch.rand(1, P * P, 1, generator=g))
+    kps1 = torch.rand(K, 3, generator=g) * 839.0
+    kps2 = torch.rand(K, 3, generator=g) * 839.0
+    kps1[:, 2] = 1.0
+    kps2[:, 2] = 1.0
+    for i in cfg["invisible"]:
+        kps2[i, 2] = 0.0
+    return d1, d1f, d2, kps1, kps2

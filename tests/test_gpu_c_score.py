@@ -96,3 +96,40 @@ def test_feature_map_layout_roundtrip():
     fmap = to_c_score_layout(f, 2, 3)                                      # extract_feature.py:82
     assert tuple(fmap.shape) == (1, 4, 2, 3)
     assert torch.equal(CS.desc_from_feature_map(fmap), f)                  # pck_train.py:38-39 undoes it
+
+
+# ---- adaptive flip / mutual-NN distance --------------------------------------------------------
+@pytest.fixture(scope="module")
+def flip_gold(golden_dir):
+    return torch.load(os.path.join(golden_dir, "c_score_flip.pt"))
+
+
+@pytest.mark.parametrize("cname", list(synth.FLIP_CASES))
+def test_adaptive_flip_matches_reference(cname, flip_gold):
+    cfg = synth.FLIP_CASES[cname]
+    d1, d1f, d2, kps1, kps2 = synth.flip_case(cfg)
+    rec = flip_gold[cname]
+    final, od, fd = CS.keypoint_transformation_adaptive_flip(d1.cuda(), d1f.cuda(), d2.cuda(), kps1, kps2, cfg["permute"])
+    # the reference's own distances come from torch.cdist's fp32 matmul form (~1e-4 on a distance): compare to it loosely and
+    # to the fp64 oracle tightly
+    assert abs(od - rec["original_dist"]) < 2e-4 and abs(fd - rec["flip_dist"]) < 2e-4
+    want_o, _ = co.mutual_nn_distance(co.normalize_feats(d1), co.normalize_feats(d2))
+    want_f, _ = co.mutual_nn_distance(co.normalize_feats(d1f), co.normalize_feats(d2))
+    assert abs(od - want_o) < 2e-5 and abs(fd - want_f) < 2e-5, (od - want_o, fd - want_f)
+    assert (fd < od) == (rec["flip_dist"] < rec["original_dist"]) == cfg["from_flip"]
+    assert (final.cpu() - rec["final"]).abs().max() < PIX_TOL
+
+
+def test_mutual_nn_batch_counts_and_dtypes():
+    g = torch.Generator().manual_seed(5)
+    P, D, B = 20, 192, 5
+    d1 = torch.randn(B, P * P, D, generator=g)
+    d2 = 0.6 * d1[:, torch.randperm(P * P, generator=g)] + 0.4 * torch.randn(B, P * P, D, generator=g)
+    d2[0] = torch.randn(P * P, D, generator=g)
+    for dt, tol in ((torch.float32, 2e-5), (torch.bfloat16, 2e-5)):
+        a, b = d1.to(dt), d2.to(dt)
+        dist, cnt = CS.get_distance_mutual_nn(a.cuda(), b.cuda(), return_count=True)
+        for i in range(B):
+            want, n = co.mutual_nn_distance(co.normalize_feats(a[i:i + 1].float()), co.normalize_feats(b[i:i + 1].float()))
+            assert int(cnt[i]) == n, (i, int(cnt[i]), n)
+            assert abs(float(dist[i]) - want) < tol, (i, float(dist[i]) - want)

@@ -64,3 +64,26 @@ def test_linear_cka_properties():
     assert abs(ao.linear_cka(X, X) - 1.0) < 1e-12
     assert abs(ao.linear_cka(X, 3.0 * X @ Q + 5.0) - 1.0) < 1e-9      # invariant to rotation, scale, shift
     assert ao.linear_cka(X, torch.randn(500, 32, generator=g)) < 0.2
+
+
+@pytest.mark.parametrize("cname", list(synth.FLIP_CASES))
+def test_adaptive_flip_oracle(cname, golden_dir):
+    """Oracle restatement of the ADAPT_FLIP + MUTUAL_NN block against the reference's own functions (c_score_flip.pt)."""
+    rec = torch.load(os.path.join(golden_dir, "c_score_flip.pt"))[cname]
+    cfg = synth.FLIP_CASES[cname]
+    d1, d1f, d2, kps1, kps2 = synth.flip_case(cfg)
+    P = cfg["P"]
+    n1, n1f, n2 = co.normalize_feats(d1), co.normalize_feats(d1f), co.normalize_feats(d2)
+    vis = kps1[:, 2] * kps2[:, 2] > 0
+    k1f = co.flip_keypoints(kps1, 840, co.permute_indices(cfg["permute"], vis))
+    assert torch.equal(k1f, rec["kps1_flip"])
+    idx_f = co.kpts_to_patch_idx(k1f, P)
+    assert torch.equal(torch.as_tensor(idx_f), rec["idx_flip"])
+    od, _ = co.mutual_nn_distance(n1, n2)
+    fd, _ = co.mutual_nn_distance(n1f, n2)
+    assert abs(od - rec["original_dist"]) < 2e-4 and abs(fd - rec["flip_dist"]) < 2e-4   # reference: fp32 matmul cdist
+    kps = co.keypoint_transformation(n1, n2, co.kpts_to_patch_idx(kps1, P), P)
+    kps_f = co.keypoint_transformation(n1f, n2, idx_f, P)
+    final = co.optimized_kps_1_to_2(kps, kps_f, kps1, kps2, fd, od, vis, cfg["permute"])
+    assert torch.allclose(final, rec["final"], rtol=1e-5, atol=2e-4)
+    assert (fd < od) == cfg["from_flip"]
