@@ -39,35 +39,55 @@ def _as_hwc_uint8(image):
     return np.ascontiguousarray(image)
 
 
-def _run(images, cfg, out_dtype, device):
+def pack_images(images):
+    """-> (pinned uint8 buffer holding the images back to back as HWC RGB, int64 byte offsets [N], int32 (H, W) [N,2])."""
     arrs = [_as_hwc_uint8(im) for im in images]
-    n = len(arrs)
-    if n == 0:
+    if not arrs:
         raise ValueError("no images")
-    L = _lib.lib()
     hw = np.array([[a.shape[0], a.shape[1]] for a in arrs], dtype=np.int32)
     sizes = [a.size for a in arrs]
-    offsets = np.zeros(n, dtype=np.int64)
+    offsets = np.zeros(len(arrs), dtype=np.int64)
     offsets[1:] = np.cumsum(sizes[:-1])
-    total = int(sum(sizes))
-    host = torch.empty(total, dtype=torch.uint8, pin_memory=True)
+    host = torch.empty(int(sum(sizes)), dtype=torch.uint8, pin_memory=torch.cuda.is_available())
     hv = host.numpy()
     for a, o in zip(arrs, offsets):
         hv[o:o + a.size] = a.reshape(-1)
-    device = torch.device(device)
-    hw_p = hw.ctypes.data_as(C.POINTER(C.c_int32))
-    need = L.lovr_preprocess_workspace_bytes(C.byref(cfg), n, hw_p)
+    return host, offsets, hw
+
+
+def workspace_bytes(cfg, hw):
+    L = _lib.lib()
+    need = L.lovr_preprocess_workspace_bytes(C.byref(cfg), len(hw), hw.ctypes.data_as(C.POINTER(C.c_int32)))
     if need == 0:
         raise _lib.LovrError("lovr_preprocess_workspace_bytes: " + L.lovr_last_error().decode("utf-8", "replace"))
+    return need
+
+
+def run_packed(dev_images, offsets, hw, cfg, out_dtype=torch.float32, out=None, ws=None):
+    """One `lovr_preprocess` call on images already resident on the device (packed like `pack_images`)."""
+    n = len(hw)
+    device = dev_images.device
+    need = workspace_bytes(cfg, hw)
+    with torch.cuda.device(device):
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(need, dtype=torch.uint8, device=device)
+        if out is None:
+            out = torch.empty(n, 3, cfg.crop_size, cfg.crop_size, dtype=out_dtype, device=device)
+        _lib.check(_lib.lib().lovr_preprocess(_lib.ptr(dev_images), offsets.ctypes.data_as(C.POINTER(C.c_int64)),
+                                              hw.ctypes.data_as(C.POINTER(C.c_int32)), n, C.byref(cfg), _lib.ptr(out),
+                                              _lib.torch_dtype_code(out.dtype), _lib.ptr(ws), ws.numel(),
+                                              _lib.stream_ptr(device)), "lovr_preprocess")
+    return out
+
+
+def _run(images, cfg, out_dtype, device):
+    host, offsets, hw = pack_images(images)
+    workspace_bytes(cfg, hw)                     # argument errors surface before any copy
+    device = torch.device(device)
     with torch.cuda.device(device):
         dev = host.to(device, non_blocking=True)
-        ws = torch.empty(need, dtype=torch.uint8, device=device)
-        out = torch.empty(n, 3, cfg.crop_size, cfg.crop_size, dtype=out_dtype, device=device)
-        _lib.check(L.lovr_preprocess(_lib.ptr(dev), offsets.ctypes.data_as(C.POINTER(C.c_int64)), hw_p, n, C.byref(cfg),
-                                     _lib.ptr(out), _lib.torch_dtype_code(out_dtype), _lib.ptr(ws), need,
-                                     _lib.stream_ptr(device)), "lovr_preprocess")
-        # ws / dev are freed to torch's caching allocator on return; later work on this stream is ordered after the kernels
-    return out
+    # dev / the workspace go back to torch's caching allocator on return; reuse is ordered after the kernels on this stream
+    return run_packed(dev, offsets, hw, cfg, out_dtype)
 
 
 class B200ImageProcessor:

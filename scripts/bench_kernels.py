@@ -55,11 +55,33 @@ def main():
     res.append(dict(kernel="attention_tcgen05", ms=ms, tflops=4 * n_img * H * T * T * 64 / ms / 1e9))
     ms = timeit(lambda: G.attention(qkv, n_img, T, H, _lib.ATTN_TCGEN05_V2))
     res.append(dict(kernel="attention2_tcgen05", ms=ms, tflops=4 * n_img * H * T * T * 64 / ms / 1e9))
+    for impl, nm in ((_lib.ATTN_TCGEN05_V2_PTMEM, "attention2_ptmem"), (_lib.ATTN_TCGEN05_V2_3PIPE, "attention2_3pipe")):
+        ms = timeit(lambda: G.attention(qkv, n_img, T, H, impl))
+        res.append(dict(kernel=nm, ms=ms, tflops=4 * n_img * H * T * T * 64 / ms / 1e9))
     g, b = torch.ones(D, device=dev), torch.zeros(D, device=dev)
     ms = timeit(lambda: G.layernorm(x, g, b, 1e-5))
     res.append(dict(kernel="layernorm", ms=ms, gbs=M * D * 6 / ms / 1e6))
+    res.append(preprocess_timing(256))
     for r in res:
         print(json.dumps(r))
+
+
+def preprocess_timing(n):
+    """lovr_preprocess on n device-resident 480x640 RGB images -> [n,3,336,336] bf16 (CLIP-336 processor):
+    algorithmic bytes = source bytes read + output bytes written."""
+    import numpy as np
+    from law_of_vision_representation_in_mllms_b200 import preprocess as PP
+    rng = np.random.default_rng(0)
+    imgs = [rng.integers(0, 256, (480, 640, 3), dtype=np.uint8) for _ in range(8)] * (n // 8)
+    host, offsets, hw = PP.pack_images(imgs)
+    dev = host.cuda()
+    proc = PP.B200ImageProcessor({"shortest_edge": 336}, 336)
+    cfg = proc._cfg()
+    ws = torch.empty(PP.workspace_bytes(cfg, hw), dtype=torch.uint8, device="cuda")
+    out = torch.empty(n, 3, 336, 336, dtype=torch.bfloat16, device="cuda")
+    ms = timeit(lambda: PP.run_packed(dev, offsets, hw, cfg, out=out, ws=ws))
+    nbytes = host.numel() + out.numel() * 2
+    return dict(kernel="preprocess_clip336_from_480x640", ms=ms, images_per_s=n / ms * 1e3, gbs=nbytes / ms / 1e6)
 
 
 if __name__ == "__main__":
