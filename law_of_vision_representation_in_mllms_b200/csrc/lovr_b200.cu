@@ -17,6 +17,7 @@
 
 #include "attention.cuh"
 #include "attention2.cuh"
+#include "attention3.cuh"
 #include "attention_simt.cuh"
 #include "cka.cuh"
 #include "cscore.cuh"
@@ -372,7 +373,31 @@ int launch_attention(const void* qkv, void* out, int n_img, int T, int H, int im
   CUtensorMap tq;
   int rc;
   if ((rc = make_tmap(&tq, qkv, 2, 3 * D, T, n_img, 3 * D, static_cast<uint64_t>(3) * D * T, 64, 128))) return rc;
-  if (impl == LOVR_ATTN_AUTO) impl = (T > 256) ? LOVR_ATTN_TCGEN05_V2_3PIPE : LOVR_ATTN_TCGEN05_V2_PTMEM;  // >= 3 query tiles
+  if (impl == LOVR_ATTN_AUTO) impl = LOVR_ATTN_TCGEN05_V3;  // fastest at T = 577, 257 and 196 (profiles/r01_attention3_ncu.md)
+  if (impl == LOVR_ATTN_TCGEN05_V3) {
+    const size_t smem3 = lovr::attn3_smem_bytes(nb);
+    // LOVR_ATTN3_PIPE (A/B switch for measurements): 0 = plain, 1 = deferred P hand-off (default)
+    const char* e_pipe = getenv("LOVR_ATTN3_PIPE");
+    const int pipe = e_pipe ? atoi(e_pipe) : lovr::kAttn3DefaultPipe;
+#define LOVR_ATTN3_LAUNCH(F16_, PIPE_)                                                                                \
+  do {                                                                                                               \
+    auto kern = lovr::attention3_tcgen05_kernel<F16_, PIPE_>;                                                        \
+    static size_t set_for3 = 0;                                                                                      \
+    if (smem3 > set_for3) {                                                                                          \
+      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem3)));    \
+      set_for3 = smem3;                                                                                              \
+    }                                                                                                                \
+    kern<<<n_img * H, lovr::kAttn3Threads, smem3, s>>>(tq, a);                                                       \
+  } while (0)
+    switch (pipe) {
+      case 0: if (f16) LOVR_ATTN3_LAUNCH(true, 0); else LOVR_ATTN3_LAUNCH(false, 0); break;
+      case 1: if (f16) LOVR_ATTN3_LAUNCH(true, 1); else LOVR_ATTN3_LAUNCH(false, 1); break;
+      default: return fail(LOVR_E_ARG, "LOVR_ATTN3_PIPE=%d: use 0 or 1", pipe);
+    }
+#undef LOVR_ATTN3_LAUNCH
+    LAUNCH_CHECK("attention3_tcgen05_kernel");
+    return 0;
+  }
   if (impl == LOVR_ATTN_TCGEN05_V2 || impl == LOVR_ATTN_TCGEN05_V2_PTMEM || impl == LOVR_ATTN_TCGEN05_V2_3PIPE) {
     const int np = impl == LOVR_ATTN_TCGEN05_V2_3PIPE ? 3 : 2;
     const bool pt = impl != LOVR_ATTN_TCGEN05_V2;

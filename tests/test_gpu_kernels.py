@@ -83,7 +83,7 @@ def test_attention_fp16_operands():
     qkv = _rand((n * T, 3 * H * 64), 31, 1.0, torch.float16)
     want = _torch_attention(qkv, n, T, H)
     for impl in (_lib.ATTN_TCGEN05, _lib.ATTN_TCGEN05_V2, _lib.ATTN_TCGEN05_V2_PTMEM, _lib.ATTN_TCGEN05_V2_3PIPE,
-                 _lib.ATTN_SIMT_CHECK):
+                 _lib.ATTN_TCGEN05_V3, _lib.ATTN_SIMT_CHECK):
         got = G.attention(qkv, n, T, H, impl)
         assert got.dtype == torch.float16
         assert G.rel_err(got, want) < 6e-4
@@ -123,7 +123,7 @@ def _torch_attention(qkv, n, T, H):
 
 
 @pytest.mark.parametrize("impl", [_lib.ATTN_SIMT_CHECK, _lib.ATTN_TCGEN05, _lib.ATTN_TCGEN05_V2, _lib.ATTN_TCGEN05_V2_PTMEM,
-                                  _lib.ATTN_TCGEN05_V2_3PIPE])
+                                  _lib.ATTN_TCGEN05_V2_3PIPE, _lib.ATTN_TCGEN05_V3])
 @pytest.mark.parametrize("n,T,H,scale", [(2, 577, 16, 1.0), (3, 257, 16, 2.0), (2, 196, 12, 1.0), (1, 50, 16, 1.0),
                                           (1, 128, 16, 3.0), (1, 640, 16, 1.0)])
 def test_attention(impl, n, T, H, scale):
