@@ -1140,7 +1140,7 @@ int lovr_cka_finalize(const double* gram, double n_rows, int32_t Dx, int32_t Dy,
 namespace {
 struct PrePlan {
   std::vector<lovr::PreImg> imgs;
-  size_t coef_off = 0, tmp_off = 0, total = 0;
+  size_t lut_off = 0, coef_off = 0, tmp_off = 0, total = 0;
   int max_rows = 0;
 };
 // Resample.c precompute_coeffs bounds of output xx (same double operations as resample_coeffs_kernel; this file is
@@ -1212,7 +1212,8 @@ int pre_plan(const lovr_preprocess_config* cfg, int32_t n_img, const int32_t* hw
     tmp_bytes += align_up(static_cast<size_t>(3) * im.rows * R, 16);
     if (im.rows > plan->max_rows) plan->max_rows = im.rows;
   }
-  plan->coef_off = align_up(static_cast<size_t>(n_img) * sizeof(lovr::PreImg), 256);
+  plan->lut_off = align_up(static_cast<size_t>(n_img) * sizeof(lovr::PreImg), 256);
+  plan->coef_off = plan->lut_off + align_up(768 * sizeof(float), 256);
   plan->tmp_off = plan->coef_off + align_up(coef_ints * 4, 256);
   plan->total = plan->tmp_off + align_up(tmp_bytes, 256);
   return 0;
@@ -1247,17 +1248,33 @@ int lovr_preprocess(const uint8_t* images, const int64_t* offsets_host, const in
   const int R = cfg->crop_size;
   lovr::resample_coeffs_kernel<<<dim3((R + 127) / 128, 2, n_img), 128, 0, s>>>(d_imgs, d_coefs, n_img, R);
   LAUNCH_CHECK("resample_coeffs_kernel");
-  const uint32_t bg = cfg->pad_rgb[0] | (cfg->pad_rgb[1] << 8) | (cfg->pad_rgb[2] << 16);
-  lovr::resample_h_kernel<<<dim3((plan.max_rows + lovr::kPreRowsPerBlock - 1) / lovr::kPreRowsPerBlock, n_img), 256, 0, s>>>(
-      images, d_imgs, d_coefs, d_tmp, R, bg);
-  LAUNCH_CHECK("resample_h_kernel");
+  float* d_lut = reinterpret_cast<float*>(ws + plan.lut_off);
   lovr::PixelMap pm;
   pm.mode = cfg->pixel_map;
   for (int c = 0; c < 3; ++c) {
     pm.mean[c] = cfg->mean[c];
     pm.stdv[c] = cfg->std[c];
   }
-  lovr::resample_v_kernel<<<dim3(R, n_img), 256, 0, s>>>(d_tmp, d_imgs, d_coefs, out, out_dtype, R, pm);
+  lovr::pixel_lut_kernel<<<3, 256, 0, s>>>(d_lut, pm);
+  LAUNCH_CHECK("pixel_lut_kernel");
+  const uint32_t bg = cfg->pad_rgb[0] | (cfg->pad_rgb[1] << 8) | (cfg->pad_rgb[2] << 16);
+  const dim3 hgrid((plan.max_rows + lovr::kPreRowsPerBlock - 1) / lovr::kPreRowsPerBlock, n_img);
+  if (cfg->pad_square)
+    lovr::resample_h_kernel<true><<<hgrid, 128, 0, s>>>(images, d_imgs, d_coefs, d_tmp, R, bg);
+  else
+    lovr::resample_h_kernel<false><<<hgrid, 128, 0, s>>>(images, d_imgs, d_coefs, d_tmp, R, bg);
+  LAUNCH_CHECK("resample_h_kernel");
+  if (R % 4 == 0) {
+    const dim3 vgrid((R * (R / 4) + 255) / 256, n_img);
+    if (out_dtype == LOVR_DT_F32)
+      lovr::resample_v4_kernel<lovr::DT_F32><<<vgrid, 256, 0, s>>>(d_tmp, d_imgs, d_coefs, d_lut, out, R);
+    else if (out_dtype == LOVR_DT_BF16)
+      lovr::resample_v4_kernel<lovr::DT_BF16><<<vgrid, 256, 0, s>>>(d_tmp, d_imgs, d_coefs, d_lut, out, R);
+    else
+      lovr::resample_v4_kernel<lovr::DT_F16><<<vgrid, 256, 0, s>>>(d_tmp, d_imgs, d_coefs, d_lut, out, R);
+  } else {
+    lovr::resample_v_kernel<<<dim3(R, n_img), 256, 0, s>>>(d_tmp, d_imgs, d_coefs, d_lut, out, out_dtype, R);
+  }
   LAUNCH_CHECK("resample_v_kernel");
   return 0;
 }

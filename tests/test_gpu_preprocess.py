@@ -46,8 +46,9 @@ def test_random_sizes_bit_exact_vs_oracle():
     for i in range(24):
         h, w = (int(v) for v in rng.integers(20, 900, 2))
         imgs.append(synth.synthetic_rgb_image(h, w, 500 + i))
+    # crop 70 / 45: not a multiple of 4 -> the one-column-per-thread vertical kernel; the others take the 4-column one
     for size, crop, exact, pad in ((64, 64, False, False), (96, 80, False, False), (112, 112, True, False),
-                                   (72, 72, False, True)):
+                                   (72, 72, False, True), (90, 70, False, False), (45, 45, True, True)):
         proc = PP.B200ImageProcessor({"height": size, "width": size} if exact else {"shortest_edge": size}, crop, mean, std)
         got = proc.preprocess(imgs, return_tensors="pt", pad_square=pad)["pixel_values"].cpu().numpy()
         for k, a in enumerate(imgs):
