@@ -33,8 +33,9 @@ enum { LOVR_EPI_BF16 = 0, LOVR_EPI_RESID_F32 = 1, LOVR_EPI_F32 = 2 };
 /* attention implementations: 0 = tcgen05, one softmax pipeline per CTA; 2 = tcgen05, single-pass online softmax, two pipelines per CTA, P via shared memory; 3 = same with P via TMEM; 4 = three pipelines, P via TMEM;
  * 1 = CUDA-core cross-check used only by tests */
 enum { LOVR_ATTN_TCGEN05 = 0, LOVR_ATTN_SIMT_CHECK = 1, LOVR_ATTN_TCGEN05_V2 = 2, LOVR_ATTN_TCGEN05_V2_PTMEM = 3,
-       LOVR_ATTN_TCGEN05_V2_3PIPE = 4, LOVR_ATTN_AUTO = 5 /* the product default: currently 6 */,
-       LOVR_ATTN_TCGEN05_V3 = 6 /* three pipelines, register-only bookkeeping, deferred P hand-off, K/V streamed per block */ };
+       LOVR_ATTN_TCGEN05_V2_3PIPE = 4, LOVR_ATTN_AUTO = 5 /* the product default: currently 7 (6 when T <= 128) */,
+       LOVR_ATTN_TCGEN05_V3 = 6 /* three pipelines, register-only bookkeeping, deferred P hand-off, K/V streamed per block */,
+       LOVR_ATTN_TCGEN05_V4 = 7 /* persistent: one CTA per SM, tiles of consecutive (image, head) items roll through the three pipelines */ };
 
 int lovr_abi_version(void);
 const char* lovr_last_error(void);

@@ -15,6 +15,7 @@ EPI_BF16, EPI_RESID_F32, EPI_F32 = 0, 1, 2
 ATTN_TCGEN05, ATTN_SIMT_CHECK, ATTN_TCGEN05_V2, ATTN_TCGEN05_V2_PTMEM, ATTN_TCGEN05_V2_3PIPE = 0, 1, 2, 3, 4
 ATTN_AUTO = 5
 ATTN_TCGEN05_V3 = 6
+ATTN_TCGEN05_V4 = 7
 RESIZE_SHORTEST_EDGE, RESIZE_EXACT = 0, 1
 PIX_HF_RESCALE_NORMALIZE, PIX_CSCORE = 0, 1
 

@@ -28,6 +28,7 @@ struct AttnArgs {
   float scale;  // head_dim^-0.5
   uint16_t* out;  // [N*T, H*64], 16-bit operand format
   long long* trace;  // debug & 8: clock64 timeline of CTA 0, pipeline 0 (diagnostics only)
+  int n_items;    // (persistent kernel) images x heads
   int debug;      // timing experiments only (LOVR_ATTN_DEBUG): 1 = skip pass 1, 2 = no ex2, 4 = skip max/exp math
 };
 

@@ -1,71 +1,32 @@
-// Fused non-causal ViT attention on tcgen05, third generation: the three-pipeline single-pass kernel of attention2.cuh
-// rebuilt from what its ncu source-level profile showed (profiles/r01_attention3_ncu.md):
-//   * every per-unit trace point read `p.debug` from LOCAL memory (the argument struct was captured by reference in
-//     lambdas, so it lived on the stack) and the fill/consume counters were stack arrays: ~8 % of the softmax warps'
-//     samples were long-scoreboard stalls on LDL.  Here the arguments are plain registers, counters are scalars and
-//     there is no tracing in the kernel: 0.285 -> 0.250 ms per 64 images, bit-identical output.
-//   * timing diagnostics (compile-time removal of one piece at a time, same launch): no exponentials -1.6 %, no
-//     tcgen05.st of P -2.4 %, no tcgen05.ld of S -10 %: no single unit is saturated; the kernel is bound by the
-//     per-unit dependency chain of a softmax warp (barrier wake-up -> TMEM load -> max -> exp -> TMEM store -> arrive).
-//     (ex2.approx.f16x2 does not help: it compiles to two MUFU.EX2.F16, one per half.)
-//   * PIPE = 1 (default) shortens that chain a little: the hand-off of P(u) (tcgen05.wait::st, fence, arrive) is deferred
-//     until the TMEM load of S(u+1) has been issued, so the store's completion latency overlaps the load's.  (Splitting the
-//     unit into two 32-column halves to overlap the second load with the first half's exponentials measured 5 % SLOWER: it
-//     delays the release of S and with it the next QK^T.)
-//   * 13-18 % of the softmax warps' samples sat in the first s_full wait of the CTA: one CTA per SM (224 KB of shared
-//     memory), so nothing overlaps the 208 KB of K, V, Q loads.  K and V now complete per 128-row block (one mbarrier
-//     each, loads issued in order of first use), so the first QK^T starts after 32 KB instead of 80 KB and the remaining
-//     blocks stream in under the first tile's compute.
-// Structure (unchanged): one CTA per (image, head); K, V resident in shared memory; query tile t -> pipeline t % 3;
-// per pipeline: S (64 columns, single buffer), O (64), P (32 packed columns) in TMEM; thread = query row.
-//   warp 0        TMA        warps 1-3   tcgen05.mma issuers of pipelines 0-2        warps 4-15  softmax (4 per pipeline)
+// Fused non-causal ViT attention on tcgen05, fourth generation: attention3's three softmax pipelines, PERSISTENT.
+//
+// attention3 runs one CTA per (image, head) and one CTA per SM (224 KB of shared memory), so every CTA pays ~5 us that
+// nothing overlaps (launch, TMEM allocation, the first K/Q loads, the last tile's epilogue, teardown: 14 % of the CTA at
+// T = 577, 40-54 % at T = 257 / 196), and its third pipeline idles while the 4th and 5th query tiles run (5 tiles on 3
+// pipelines).  Here one CTA per SM walks a list of items (image, head) and its query tiles form ONE rolling sequence,
+// tile s -> pipeline s % 3, across item boundaries:
+//   * K and V stay single-buffered (160 KB), but every 128-row block has its own full/free mbarrier pair: a tile's MMA
+//     issuer commits `k_free[j]` / `v_free[j]` once it is past block j, and when all tiles of the item have done so the
+//     TMA warp loads the NEXT item's block j into the same shared memory.  The next item's first tile therefore starts
+//     while the current item's last tiles are still running (trailing them by ~3 units), and no pipeline idles.
+//   * the TMA warp is one polling loop over every pending request (Q tile per pipeline, next K block, next V block), so
+//     no request waits behind another.
+//   * TMEM, barriers and setmaxnreg are set up once per SM.
+// Up to three items can be in flight when an item has two query tiles (T <= 256); the block-full barriers therefore
+// alternate between two sets (see below).  T <= 128 (one tile per item, one K/V block) keeps the attention3 kernel.
+// Register split (setmaxnreg): 80 for the four control warps, 144 for the twelve softmax warps.  Measured per 64 images
+// at T = 577 with control budgets 40 / 56 / 80 / 104 / 128 (no rebalancing): 0.240 / 0.217 / 0.209 / 0.240 / 0.314 ms — at 40
+// registers the MMA issue loop spills to local memory, and the issuer's loop time is on the critical path.
 #pragma once
-#include <cuda_fp16.h>
-
-#include "attention2.cuh"
+#include "attention3.cuh"
 
 namespace lovr {
 
-constexpr int kAttn3Threads = 16 * 32;
-constexpr int kAttn3PipeCols = 160;  // S [0,64) | O [64,128) | P [128,160)
-constexpr int kAttn3DefaultPipe = 1;
+constexpr int kAttn4ControlRegs = 80;
 
-inline size_t attn3_smem_bytes(int nb) { return static_cast<size_t>(2 * nb + 3) * 16384 + 512 + 1024; }
-
-// P = exp2(s*c1 - mc) for one 32-column half held in registers (thread = row); row sums into l0/l1; 16 packed pairs.
-template <bool F16, bool MASK>
-__device__ __forceinline__ void attn3_exp_half(const uint32_t (&buf)[32], int valid, float c1, float mc, float& l0,
-                                               float& l1, uint32_t* pk) {
-#pragma unroll
-  for (int i = 0; i < 32; i += 2) {
-    float e0 = ex2_approx(fmaf(__uint_as_float(buf[i]), c1, -mc));
-    float e1 = ex2_approx(fmaf(__uint_as_float(buf[i + 1]), c1, -mc));
-    if constexpr (MASK) {
-      e0 = (i < valid) ? e0 : 0.f;
-      e1 = (i + 1 < valid) ? e1 : 0.f;
-    }
-    l0 += e0;
-    l1 += e1;
-    pk[i >> 1] = pack16x2<F16>(e0, e1);
-  }
-}
-
-template <bool MASK>
-__device__ __forceinline__ float attn3_max_half(const uint32_t (&buf)[32], int valid) {
-  float a0 = -INFINITY, a1 = a0, a2 = a0, a3 = a0;
-#pragma unroll
-  for (int e = 0; e < 32; e += 4) {
-    if (!MASK || e < valid) a0 = fmaxf(a0, __uint_as_float(buf[e]));
-    if (!MASK || e + 1 < valid) a1 = fmaxf(a1, __uint_as_float(buf[e + 1]));
-    if (!MASK || e + 2 < valid) a2 = fmaxf(a2, __uint_as_float(buf[e + 2]));
-    if (!MASK || e + 3 < valid) a3 = fmaxf(a3, __uint_as_float(buf[e + 3]));
-  }
-  return fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
-}
-
-template <bool F16, int PIPE>
+template <bool F16, int RC>  // RC = registers of the four control warps; the softmax warps get (65536 - 128 RC) / 384
 __global__ void __launch_bounds__(kAttn3Threads, 1)
-attention3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs p) {
+attention4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int NP = 3;
@@ -76,21 +37,48 @@ attention3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
   uint8_t* sV = sK + nb * 16384;
   uint8_t* sQ = sV + nb * 16384;  // [3 pipelines] x 16 KB
   uint64_t* bars = reinterpret_cast<uint64_t*>(sQ + NP * 16384);
-  // barriers: k_full[5] (one per 128-row K block, so the first QK^T starts after 16 KB, not 80 KB), v_full[5], then per
-  // pipeline g (base kPipeBar + 8 g): q_full, q_empty, s_full, s_empty, p_full, p_empty, o_full, o_empty
-  constexpr int kPipeBar = 2 * kAttnMaxBlocks;
+  // barriers per 128-row block j: k_full[j] (TMA -> QK^T issuers), k_free[j] (every tile of the item has retired its QK^T
+  // on the block: the next item's block may land), v_full[j], v_free[j]; then per pipeline g (base kPipeBar + 8 g):
+  // q_full, q_empty, s_full, s_empty, p_full, p_empty, o_full, o_empty
+  // Three consecutive tiles are in flight.  With >= 3 tiles per item they span two items and the parity of a block's fill
+  // identifies the item.  With two tiles per item (T <= 256) they can span three: a tile of item i can reach a block
+  // while item i-1's fill is still pending and the block holds item i-2, whose "fill complete" has the parity it waits
+  // for.  Then the full barriers alternate between two sets (even / odd items): the fill of item i is phase i/2 of set
+  // i%2 and the nearest earlier fill with the same parity is four items back.
+  // Layout note: the placement of these 8-byte objects is measurable.  With the first set, the free barriers and the
+  // pipeline groups packed as below the kernel runs 0.230 ms per 64 images at T = 577; with the two full sets placed first
+  // (or every pipeline group padded to its own 128-byte line) 0.242 ms — same code otherwise.  The second set, only used
+  // when an item has two tiles, therefore sits behind the pipeline groups.
+  constexpr int kPipeBar = 4 * kAttnMaxBlocks;
+  constexpr int kSet1 = kPipeBar + 8 * NP;        // second set of full barriers: k at kSet1 + j, v at kSet1 + 5 + j
   uint64_t* k_full = bars + 0;
-  uint64_t* v_full = bars + kAttnMaxBlocks;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kPipeBar + 8 * NP);
+  uint64_t* k_free = bars + kAttnMaxBlocks;
+  uint64_t* v_full = bars + 2 * kAttnMaxBlocks;
+  uint64_t* v_free = bars + 3 * kAttnMaxBlocks;
+  uint64_t* k_full1 = bars + kSet1;
+  uint64_t* v_full1 = bars + kSet1 + kAttnMaxBlocks;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kSet1 + 2 * kAttnMaxBlocks);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n = blockIdx.x / H, h = blockIdx.x % H;
   const int D = H * 64;
   const int q_tiles = (T + 127) / 128;
+  // this CTA's items: blockIdx.x, blockIdx.x + gridDim.x, ...; its tiles in one rolling sequence, tile s -> pipeline s % 3
+  const int my_items = (p.n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int total_tiles = my_items * q_tiles;
+  const bool two_sets = q_tiles < 3;  // see the barrier comment above: three tiles in flight span three items only then
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQKV);
-    for (int j = 0; j < 2 * kAttnMaxBlocks; ++j) mbar_init(bars + j, 1);
+    for (int j = 0; j < kAttnMaxBlocks; ++j) {
+      mbar_init(k_full + j, 1);
+      mbar_init(v_full + j, 1);
+      mbar_init(k_full1 + j, 1);
+      mbar_init(v_full1 + j, 1);
+    }
+    for (int j = 0; j < kAttnMaxBlocks; ++j) {
+      mbar_init(k_free + j, q_tiles);  // one tcgen05.commit per tile of the item
+      mbar_init(v_free + j, q_tiles);
+    }
     for (int g = 0; g < NP; ++g) {
       uint64_t* b = bars + kPipeBar + 8 * g;
       mbar_init(b + 0, 1);  // q_full
@@ -114,37 +102,57 @@ attention3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(80));  // 40 spills the MMA issue loop: see attention4.cuh
+    if constexpr (RC < 128) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(RC));
     if (warp == 0) {
       // ===================================================================== TMA
       if (lane == 0) {
-        // issue order = order of first use: Q0, K0, Q1, Q2, then K and V blocks alternating
-        auto load_q = [&](int g, int t) {
-          mbar_arrive_expect_tx(bars + kPipeBar + 8 * g, 16384);
-          tma_load_3d(sQ + g * 16384, &tmQKV, bars + kPipeBar + 8 * g, h * 64, t * 128, n);
-        };
-        auto load_k = [&](int j) {
-          mbar_arrive_expect_tx(k_full + j, 16384);
-          tma_load_3d(sK + j * 16384, &tmQKV, k_full + j, D + h * 64, j * 128, n);
-        };
-        auto load_v = [&](int j) {
-          mbar_arrive_expect_tx(v_full + j, 16384);
-          tma_load_3d(sV + j * 16384, &tmQKV, v_full + j, 2 * D + h * 64, j * 128, n);
-        };
-        load_q(0, 0);
-        load_k(0);
-        for (int g = 1; g < NP; ++g)
-          if (g < q_tiles) load_q(g, g);
-        load_v(0);
-        for (int j = 1; j < nb; ++j) {
-          load_k(j);
-          load_v(j);
-        }
-        // remaining Q tiles in tile order: tile t waits for the QK^T of tile t - 3 (same pipeline) to retire
-        for (int t = NP; t < q_tiles; ++t) {
-          const int g = t % NP, k = t / NP;
-          mbar_wait(bars + kPipeBar + 8 * g + 1, (k - 1) & 1);
-          load_q(g, t);
+        // One polling loop serves every pending request so that no pipeline waits behind another one's load:
+        //   Q tile of pipeline g (needs the QK^T of that pipeline's previous tile retired),
+        //   next K block / next V block in (item, block) order (needs the previous item's tiles past that block).
+        int q_next[NP], q_cnt[NP];
+        for (int g = 0; g < NP; ++g) { q_next[g] = g; q_cnt[g] = 0; }
+        int k_item = 0, k_blk = 0, v_item = 0, v_blk = 0;
+        const long long t0 = clock64();
+        for (;;) {
+          bool pending = false;
+          for (int g = 0; g < NP; ++g) {
+            const int s = q_next[g];
+            if (s >= total_tiles) continue;
+            pending = true;
+            uint64_t* b = bars + kPipeBar + 8 * g;
+            if (q_cnt[g] == 0 || mbar_try_wait(b + 1, (q_cnt[g] - 1) & 1)) {
+              const int item = static_cast<int>(blockIdx.x) + (s / q_tiles) * static_cast<int>(gridDim.x);
+              mbar_arrive_expect_tx(b + 0, 16384);
+              tma_load_3d(sQ + g * 16384, &tmQKV, b + 0, (item % H) * 64, (s % q_tiles) * 128, item / H);
+              q_next[g] += NP;
+              ++q_cnt[g];
+            }
+          }
+          if (k_item < my_items) {
+            pending = true;
+            if (k_item == 0 || mbar_try_wait(k_free + k_blk, (k_item - 1) & 1)) {
+              const int item = static_cast<int>(blockIdx.x) + k_item * static_cast<int>(gridDim.x);
+              uint64_t* full = ((two_sets && (k_item & 1)) ? k_full1 : k_full) + k_blk;
+              mbar_arrive_expect_tx(full, 16384);
+              tma_load_3d(sK + k_blk * 16384, &tmQKV, full, D + (item % H) * 64, k_blk * 128, item / H);
+              if (++k_blk == nb) { k_blk = 0; ++k_item; }
+            }
+          }
+          if (v_item < my_items) {
+            pending = true;
+            if (v_item == 0 || mbar_try_wait(v_free + v_blk, (v_item - 1) & 1)) {
+              const int item = static_cast<int>(blockIdx.x) + v_item * static_cast<int>(gridDim.x);
+              uint64_t* full = ((two_sets && (v_item & 1)) ? v_full1 : v_full) + v_blk;
+              mbar_arrive_expect_tx(full, 16384);
+              tma_load_3d(sV + v_blk * 16384, &tmQKV, full, 2 * D + (item % H) * 64, v_blk * 128, item / H);
+              if (++v_blk == nb) { v_blk = 0; ++v_item; }
+            }
+          }
+          if (!pending) break;
+          if (clock64() - t0 > 4 * LOVR_SPIN_LIMIT_CYCLES) {
+            printf("lovr: attention4 TMA poll timed out (block %d)\n", blockIdx.x);
+            __trap();
+          }
         }
       }
     } else {
@@ -172,12 +180,17 @@ attention3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
       uint32_t n_s = 0;  // QK^T units issued (S fills)
       uint32_t n_p = 0;  // P units consumed
       int k = 0;
-      for (int t = g; t < q_tiles; t += NP, ++k) {
+      for (int s = g; s < total_tiles; s += NP, ++k) {
+        const int il = s / q_tiles;                                  // this CTA's il-th item
+        const bool set1 = two_sets && (il & 1);                      // barrier set and parity of its K/V block fills
+        uint64_t* const kf = set1 ? k_full1 : k_full;
+        uint64_t* const vf = set1 ? v_full1 : v_full;
+        const uint32_t kv_par = static_cast<uint32_t>(two_sets ? (il >> 1) : il) & 1u;
         mbar_wait(q_full, k & 1);
         for (int u = 0; u <= nu; ++u) {
           // QK^T(u) goes first: S(u-1) is already in the softmax warps' registers, so it runs while they exponentiate
           if (u < nu) {
-            if (k == 0) mbar_wait(k_full + (u >> 1), 0);  // first tile of the CTA: K block u/2 has landed
+            mbar_wait(kf + (u >> 1), kv_par);  // this item's K block u/2 has landed
             mbar_wait(s_empty, (n_s & 1) ^ 1);
             tc_fence_after();
             if (lane == 0) {
@@ -188,6 +201,7 @@ attention3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
                 umma_bf16_ss(tS, smem_desc_join(kHi, q_lo + 2 * kk), smem_desc_join(kHi, k_lo + 2 * kk), idesc, kk != 0);
               umma_commit(s_full);
               if (u == nu - 1) umma_commit(q_empty);  // every QK^T of this tile issued: Q may be overwritten once they retire
+              if ((u & 1) || u == nu - 1) umma_commit(k_free + (u >> 1));  // this tile is past K block u/2
             }
             __syncwarp();
             ++n_s;
@@ -198,7 +212,7 @@ attention3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
           } else {
             // P·V(u-1)
             const int up = u - 1;
-            if (k == 0) mbar_wait(v_full + (up >> 1), 0);
+            mbar_wait(vf + (up >> 1), kv_par);
             mbar_wait(p_full, n_p & 1);
             tc_fence_after();
             if (lane == 0) {
@@ -208,6 +222,7 @@ attention3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
                 umma_bf16_ts(tO, tP + s * 8, smem_desc_join(kHi, v_lo + s * (2048 >> 4)), idesc_o,
                              (up == 0 && s == 0) ? 0u : 1u);
               umma_commit(p_empty);
+              if ((up & 1) || up == nu - 1) umma_commit(v_free + (up >> 1));
               if (up == nu - 1) umma_commit(o_full);
             }
             __syncwarp();
@@ -218,7 +233,7 @@ attention3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
     }
   } else {
     // ===================================================================== softmax pipelines
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(144));
+    if constexpr (RC < 128) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"((65536 - 128 * RC) / 384 / 8 * 8));
     const int g = (warp - 4) >> 2;
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
@@ -268,10 +283,12 @@ attention3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
       }
       return alpha;
     };
-    for (int t = g; t < q_tiles; t += NP, ++k) {
+    for (int s = g; s < total_tiles; s += NP, ++k) {
+      const int item = static_cast<int>(blockIdx.x) + (s / q_tiles) * static_cast<int>(gridDim.x);
+      const int n = item / H, h = item % H, t = s % q_tiles;
       float m_used = 0.f;  // row maximum (raw score units) the exponentials are currently taken against
       float l0 = 0.f, l1 = 0.f;
-      bool pending = false;  // PIPE >= 1: P(u-1) stored to TMEM but not yet handed off
+      bool pending = false;  // P(u-1) stored to TMEM but not yet handed off
       for (int u = 0; u < nu; ++u) {
         const int w = (u == nu - 1) ? last_w : 64;
         const int valid = min(64, T - u * 64);
@@ -279,7 +296,7 @@ attention3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
         tc_fence_after();
         tmem_ld_32x32b_x32(tS, buf[0]);
         if (w == 64) tmem_ld_32x32b_x32(tS + 32, buf[1]);
-        if (PIPE >= 1 && pending) hand_off();  // overlaps the load latency
+        if (pending) hand_off();  // overlaps the load latency
         tmem_ld_wait_dep(buf[0]);
         {
           if (w == 64) tmem_ld_wait_dep(buf[1]);
@@ -317,10 +334,9 @@ attention3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
         mbar_wait(p_empty, (n_p & 1) ^ 1);
         tmem_st_32x32b_x32(tPw, pk);  // 64 P values of this row as 32 packed columns
         ++n_p;
-        if constexpr (PIPE >= 1) pending = true;
-        else hand_off();
+        pending = true;
       }
-      if (PIPE >= 1 && pending) hand_off();
+      if (pending) hand_off();
       // ---------------- O / l -> global
       mbar_wait(o_full, k & 1);
       tc_fence_after();

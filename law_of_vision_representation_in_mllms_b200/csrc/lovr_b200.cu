@@ -18,6 +18,7 @@
 #include "attention.cuh"
 #include "attention2.cuh"
 #include "attention3.cuh"
+#include "attention4.cuh"
 #include "attention_simt.cuh"
 #include "cka.cuh"
 #include "cscore.cuh"
@@ -357,6 +358,7 @@ int launch_attention(const void* qkv, void* out, int n_img, int T, int H, int im
   a.nu = (T + 63) / 64;
   a.last_w64 = (T - 64 * (a.nu - 1) + 31) / 32 * 32;
   a.out = static_cast<uint16_t*>(out);
+  a.n_items = n_img * H;
   {
     const char* dbg = getenv("LOVR_ATTN_DEBUG");
     a.debug = dbg ? atoi(dbg) : 0;
@@ -373,7 +375,26 @@ int launch_attention(const void* qkv, void* out, int n_img, int T, int H, int im
   CUtensorMap tq;
   int rc;
   if ((rc = make_tmap(&tq, qkv, 2, 3 * D, T, n_img, 3 * D, static_cast<uint64_t>(3) * D * T, 64, 128))) return rc;
-  if (impl == LOVR_ATTN_AUTO) impl = LOVR_ATTN_TCGEN05_V3;  // fastest at T = 577, 257 and 196 (profiles/r01_attention3_ncu.md)
+  if (impl == LOVR_ATTN_AUTO) impl = LOVR_ATTN_TCGEN05_V4;  // fastest at T = 577, 257 and 196 (profiles/r01_attention_ncu.md)
+  if (impl == LOVR_ATTN_TCGEN05_V4 && nb < 2) impl = LOVR_ATTN_TCGEN05_V3;  // one query tile per item: see attention4.cuh
+  if (impl == LOVR_ATTN_TCGEN05_V4) {
+    const size_t smem4 = lovr::attn3_smem_bytes(nb);
+    const int grid = a.n_items < device_info().sms ? a.n_items : device_info().sms;
+#define LOVR_ATTN4_LAUNCH(F16_, RC_)                                                                                  \
+  do {                                                                                                               \
+    auto kern = lovr::attention4_tcgen05_kernel<F16_, RC_>;                                                             \
+    static size_t set_for4 = 0;                                                                                      \
+    if (smem4 > set_for4) {                                                                                          \
+      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem4)));    \
+      set_for4 = smem4;                                                                                              \
+    }                                                                                                                \
+    kern<<<grid, lovr::kAttn3Threads, smem4, s>>>(tq, a);                                                            \
+  } while (0)
+    if (f16) LOVR_ATTN4_LAUNCH(true, lovr::kAttn4ControlRegs); else LOVR_ATTN4_LAUNCH(false, lovr::kAttn4ControlRegs);
+#undef LOVR_ATTN4_LAUNCH
+    LAUNCH_CHECK("attention4_tcgen05_kernel");
+    return 0;
+  }
   if (impl == LOVR_ATTN_TCGEN05_V3) {
     const size_t smem3 = lovr::attn3_smem_bytes(nb);
     // LOVR_ATTN3_PIPE (A/B switch for measurements): 0 = plain, 1 = deferred P hand-off (default)

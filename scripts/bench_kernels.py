@@ -56,7 +56,7 @@ def main():
     ms = timeit(lambda: G.attention(qkv, n_img, T, H, _lib.ATTN_TCGEN05_V2))
     res.append(dict(kernel="attention2_tcgen05", ms=ms, tflops=4 * n_img * H * T * T * 64 / ms / 1e9))
     for impl, nm in ((_lib.ATTN_TCGEN05_V2_PTMEM, "attention2_ptmem"), (_lib.ATTN_TCGEN05_V2_3PIPE, "attention2_3pipe"),
-                     (_lib.ATTN_TCGEN05_V3, "attention3 (default)")):
+                     (_lib.ATTN_TCGEN05_V3, "attention3"), (_lib.ATTN_TCGEN05_V4, "attention4 persistent (default)")):
         ms = timeit(lambda: G.attention(qkv, n_img, T, H, impl))
         res.append(dict(kernel=nm, ms=ms, tflops=4 * n_img * H * T * T * 64 / ms / 1e9))
     g, b = torch.ones(D, device=dev), torch.zeros(D, device=dev)

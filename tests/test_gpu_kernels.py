@@ -83,7 +83,7 @@ def test_attention_fp16_operands():
     qkv = _rand((n * T, 3 * H * 64), 31, 1.0, torch.float16)
     want = _torch_attention(qkv, n, T, H)
     for impl in (_lib.ATTN_TCGEN05, _lib.ATTN_TCGEN05_V2, _lib.ATTN_TCGEN05_V2_PTMEM, _lib.ATTN_TCGEN05_V2_3PIPE,
-                 _lib.ATTN_TCGEN05_V3, _lib.ATTN_SIMT_CHECK):
+                 _lib.ATTN_TCGEN05_V3, _lib.ATTN_TCGEN05_V4, _lib.ATTN_SIMT_CHECK):
         got = G.attention(qkv, n, T, H, impl)
         assert got.dtype == torch.float16
         assert G.rel_err(got, want) < 6e-4
@@ -123,7 +123,7 @@ def _torch_attention(qkv, n, T, H):
 
 
 @pytest.mark.parametrize("impl", [_lib.ATTN_SIMT_CHECK, _lib.ATTN_TCGEN05, _lib.ATTN_TCGEN05_V2, _lib.ATTN_TCGEN05_V2_PTMEM,
-                                  _lib.ATTN_TCGEN05_V2_3PIPE, _lib.ATTN_TCGEN05_V3])
+                                  _lib.ATTN_TCGEN05_V2_3PIPE, _lib.ATTN_TCGEN05_V3, _lib.ATTN_TCGEN05_V4])
 @pytest.mark.parametrize("n,T,H,scale", [(2, 577, 16, 1.0), (3, 257, 16, 2.0), (2, 196, 12, 1.0), (1, 50, 16, 1.0),
                                           (1, 128, 16, 3.0), (1, 640, 16, 1.0)])
 def test_attention(impl, n, T, H, scale):
@@ -143,3 +143,15 @@ def test_attention_tcgen05_matches_simt_check():
     c = G.attention(qkv, n, T, H, _lib.ATTN_TCGEN05_V2)
     assert G.rel_err(a, b.float()) < 4e-3
     assert G.rel_err(c, b.float()) < 4e-3
+
+
+@pytest.mark.parametrize("n,T,H", [(40, 577, 16), (70, 257, 16), (100, 196, 12), (19, 640, 16), (10, 300, 16)])
+def test_persistent_attention_many_items(n, T, H):
+    """attention4: more (image, head) items than SMs, so every CTA rolls several items through its three pipelines; the
+    per-tile arithmetic is attention3's, so the two must agree bit for bit, and both with the fp32 reference."""
+    qkv = _rand((n * T, 3 * H * 64), 7 + T, 1.5)
+    got = G.attention(qkv, n, T, H, _lib.ATTN_TCGEN05_V4)
+    assert torch.equal(got, G.attention(qkv, n, T, H, _lib.ATTN_TCGEN05_V3))
+    assert G.rel_err(got, _torch_attention(qkv, n, T, H)) < 4e-3
+    for _ in range(3):     # no state leaks between launches
+        assert torch.equal(G.attention(qkv, n, T, H, _lib.ATTN_TCGEN05_V4), got)

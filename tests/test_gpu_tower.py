@@ -94,7 +94,7 @@ def test_tower_matches_oracle_full_tensor_and_simt_attention(cname):
     errs = {}
     for name_, impl in (("simt", _lib.ATTN_SIMT_CHECK), ("tcgen05_v1", _lib.ATTN_TCGEN05), ("tcgen05_v2_smemP", _lib.ATTN_TCGEN05_V2),
                         ("tcgen05_v2_tmemP", _lib.ATTN_TCGEN05_V2_PTMEM), ("tcgen05_v2_3pipe", _lib.ATTN_TCGEN05_V2_3PIPE),
-                        ("tcgen05_v3", _lib.ATTN_TCGEN05_V3)):
+                        ("tcgen05_v3", _lib.ATTN_TCGEN05_V3), ("tcgen05_v4_persistent", _lib.ATTN_TCGEN05_V4)):
         tower._attn_impl = impl
         errs[name_] = G.rel_err(tower(imgs.cuda()).cpu(), want)
     print(f"{cname}: default attention {e1:.3e}, others {errs}")
