@@ -155,7 +155,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="images per step per GPU")
     ap.add_argument("--chunk", type=int, default=128, help="images per native tower call")
-    ap.add_argument("--cpu-images", type=int, default=8, help="images per CPU-baseline sample / reference-arm step")
+    ap.add_argument("--cpu-images", type=int, default=32, help="images per CPU-baseline sample / reference-arm step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-a-score", action="store_true")
     ap.add_argument("--operand-dtype", default="bf16", choices=["bf16", "fp16"],
@@ -299,6 +299,55 @@ def main():
                                  dense_tflops=2.0 * Pg ** 4 * D * npairs_dense / (dense_ms / 1e3) / 1e12,
                                  keypoint_path_us_per_pair=1e3 * kp_ms / npairs_kp)
         del d1, d2
+        # ---- rows measured beside the headline (SURVEY.md §8f / configs[3]): GPU image preprocessing and the dual-tower
+        # clip336.dinov2-large extract + fused concat, both with device-resident inputs
+        import numpy as np
+        from law_of_vision_representation_in_mllms_b200 import preprocess as PP
+        rng = np.random.default_rng(rank)
+        raw = [rng.integers(0, 256, (480, 640, 3), dtype=np.uint8) for _ in range(8)] * 32
+        host_raw, offs, hw = PP.pack_images(raw)
+        dev_raw = host_raw.to(dev)
+        pcfg = tower.image_processor._cfg()
+        pws = torch.empty(PP.workspace_bytes(pcfg, hw), dtype=torch.uint8, device=dev)
+        pout = torch.empty(len(raw), 3, R, R, dtype=io_dtype, device=dev)
+        for _ in range(3):
+            PP.run_packed(dev_raw, offs, hw, pcfg, out=pout, ws=pws)
+        barrier()
+        e0.record()
+        for _ in range(5):
+            PP.run_packed(dev_raw, offs, hw, pcfg, out=pout, ws=pws)
+        e1.record()
+        barrier()
+        pre_ms = e0.elapsed_time(e1) / 5
+        a_info["preprocess"] = dict(
+            config="256 x 480x640 8-bit RGB -> CLIP-336 pixels on the device (Pillow-exact bicubic, centre crop, HF normalise), per GPU",
+            images_per_s=len(raw) / pre_ms * 1e3, hbm_gbs=(host_raw.numel() + pout.numel() * 2) / pre_ms / 1e6)
+        del dev_raw, pws, pout
+        ex2 = X.build_extractor("openai/clip-vit-large-patch14-336.facebook/dinov2-large", chunk=args.chunk,
+                                lovr_max_batch=args.chunk, lovr_device=dev, lovr_seed=0, lovr_image_size=R,
+                                lovr_operand_dtype=args.operand_dtype)
+        n2 = args.chunk
+        out2 = torch.empty(n2, T_PATCH, 2 * D, dtype=io_dtype, device=dev)
+
+        def dual(i):
+            off = 0
+            for tw in ex2.towers:
+                tw.forward_into(dev_px[i % n_in][:n2], out2, off)
+                off += tw.hidden_size
+        for i in range(2):
+            dual(i)
+        barrier()
+        e0.record()
+        for i in range(4):
+            dual(i)
+        e1.record()
+        barrier()
+        dual_ms = torch.tensor([e0.elapsed_time(e1) / 4], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dual_ms, op=dist.ReduceOp.MAX)
+        a_info["dual_tower"] = dict(config="clip336.dinov2-large @336 extract + fused concat -> [N,576,2048] (configs[3] shape)",
+                                    images_per_s=world * n2 / dual_ms.item() * 1e3)
+        del ex2, out2
 
     if rank == 0:
         peaks = measured_peaks()
@@ -320,7 +369,7 @@ def main():
             roofline=dict(bound="tensor", kernel="gemm_tcgen05_kernel (all dense layers)", achieved=achieved,
                           peak=peaks["tflops"], unit="TFLOP/s", frac=achieved / peaks["tflops"], peak_source=peaks["source"],
                           launches=gemm_launches, gemm_share_of_step=gemm_ms / ms,
-                          traffic=(792e6 if args.chunk == 128 else None),
+                          traffic=(807e6 if args.chunk == 128 else None),
                           traffic_note="avg DRAM read+write bytes per dense-layer GEMM launch at 128 images (ncu --set full, "
                                        "profiles/r01_ncu_summary_final.md)",
                           whole_step_tflops=value / world * FLOPS_PER_IMAGE / 1e12),
