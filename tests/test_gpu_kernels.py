@@ -145,7 +145,8 @@ def test_attention_tcgen05_matches_simt_check():
     assert G.rel_err(c, b.float()) < 4e-3
 
 
-@pytest.mark.parametrize("n,T,H", [(40, 577, 16), (70, 257, 16), (100, 196, 12), (19, 640, 16), (10, 300, 16)])
+@pytest.mark.parametrize("n,T,H", [(40, 577, 16), (70, 257, 16), (100, 196, 12), (19, 640, 16), (10, 300, 16),
+                                   (23, 129, 16), (31, 256, 12), (13, 384, 16), (11, 513, 16), (29, 200, 16), (10, 128, 16)])
 def test_persistent_attention_many_items(n, T, H):
     """attention4: more (image, head) items than SMs, so every CTA rolls several items through its three pipelines; the
     per-tile arithmetic is attention3's, so the two must agree bit for bit, and both with the fp32 reference."""
