@@ -323,6 +323,23 @@ def main():
             config="256 x 480x640 8-bit RGB -> CLIP-336 pixels on the device (Pillow-exact bicubic, centre crop, HF normalise), per GPU",
             images_per_s=len(raw) / pre_ms * 1e3, hbm_gbs=(host_raw.numel() + pout.numel() * 2) / pre_ms / 1e6)
         del dev_raw, pws, pout
+        # the same end-to-end path as `e2e`, but from raw 8-bit images: host packing + H2D of bytes + GPU preprocessing +
+        # tower + D2H (extract.FeatureExtractor.run_images), i.e. what replaces the reference's CPU DataLoader preprocessing
+        ex.run_images(raw, host_out, pixel_dtype=io_dtype)
+        barrier()
+        t_raw = time.perf_counter()
+        e0.record()
+        for _ in range(3):
+            ex.run_images(raw, host_out, pixel_dtype=io_dtype)
+        e1.record()
+        barrier()
+        raw_ms = torch.tensor([e0.elapsed_time(e1) / 3], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(raw_ms, op=dist.ReduceOp.MAX)
+        a_info["e2e_from_raw_images"] = dict(
+            api="extract.FeatureExtractor.run_images (256 x 480x640 8-bit RGB on the host -> features on the host)",
+            images_per_s=world * len(raw) / raw_ms.item() * 1e3, h2d_bytes_per_step=int(host_raw.numel()),
+            host_wall_ms_per_step=(time.perf_counter() - t_raw) * 1e3 / 3)
         ex2 = X.build_extractor("openai/clip-vit-large-patch14-336.facebook/dinov2-large", chunk=args.chunk,
                                 lovr_max_batch=args.chunk, lovr_device=dev, lovr_seed=0, lovr_image_size=R,
                                 lovr_operand_dtype=args.operand_dtype)

@@ -109,6 +109,56 @@ class FeatureExtractor:
         return host_out
 
 
+    @torch.no_grad()
+    def run_images(self, images, host_out=None, pixel_dtype=torch.bfloat16, pad_square=False):
+        """Raw images (PIL images or HWC uint8 arrays, any sizes) -> pinned CPU features [N,P,sum(hidden)].
+
+        The reference preprocesses on the CPU (DataLoader workers + HF processors, llava/feature/extract.py:176-190;
+        `process_images`, llava/mm_utils.py:78-95) and copies float pixels to the GPU.  Here the 8-bit images are packed and
+        copied as they are (half the bytes of bf16 pixels) and every tower's own processor configuration runs on the
+        device (`lovr_preprocess`, bit-identical pixel values); packing chunk i+1 on the host overlaps the device work
+        of chunk i because nothing in the loop synchronises."""
+        from . import preprocess as PP
+        n = len(images)
+        if n == 0:
+            raise ValueError("no images")
+        procs = [t.image_processor for t in self.towers]
+        sizes = [p.crop_size["height"] for p in procs]
+        toks = {t.out_tokens(r) for t, r in zip(self.towers, sizes)}
+        if len(toks) != 1:
+            raise RuntimeError(f"towers disagree on token count: {sorted(toks)}")
+        P, Dtot = toks.pop(), sum(t.hidden_size for t in self.towers)
+        out_dtype = self.out_dtype or pixel_dtype
+        if host_out is None:
+            host_out = torch.empty(n, P, Dtot, dtype=out_dtype, pin_memory=True)
+        c = min(self.chunk, n)
+        b = self._alloc([(c, 3, r, r) for r in sizes], pixel_dtype, (c, P, Dtot), out_dtype)
+        main = torch.cuda.current_stream(self.device)
+        for k in range(2):
+            b["out_free"][k].record(main)
+        for i, s in enumerate(range(0, n, c)):
+            e, k = min(n, s + c), i & 1
+            host_raw, offsets, hw = PP.pack_images(images[s:e])
+            with torch.cuda.stream(self._copy_in):
+                dev_raw = host_raw.to(self.device, non_blocking=True)
+                b["in_ready"][k].record(self._copy_in)
+            dev_raw.record_stream(main)
+            main.wait_event(b["in_ready"][k])
+            main.wait_event(b["out_free"][k])
+            off = 0
+            for t, p, d in zip(self.towers, procs, b["px"][k]):
+                PP.run_packed(dev_raw, offsets, hw, p._cfg(pad_square), out=d[: e - s])
+                t.forward_into(d[: e - s], b["out"][k][: e - s], off)
+                off += t.hidden_size
+            b["fwd_done"][k].record(main)
+            with torch.cuda.stream(self._copy_out):
+                self._copy_out.wait_event(b["fwd_done"][k])
+                host_out[s:e].copy_(b["out"][k][: e - s], non_blocking=True)
+                b["out_free"][k].record(self._copy_out)
+        main.wait_stream(self._copy_out)
+        return host_out
+
+
 def build_extractor(selector, select_layer=-2, select_feature="patch", chunk=64, **tower_args):
     """`--vision_tower` string -> towers (llava_arch.py grammar) -> FeatureExtractor."""
     import types

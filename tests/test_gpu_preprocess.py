@@ -84,3 +84,23 @@ def test_errors():
         proc.preprocess([synth.synthetic_rgb_image(40, 50, 1)])
     with pytest.raises(ValueError):
         PP.B200ImageProcessor({"shortest_edge": 32}, 32).preprocess([np.zeros((4, 4), np.uint8)])
+
+
+def test_extractor_from_raw_images_equals_preprocess_then_tower():
+    """FeatureExtractor.run_images (8-bit images in, GPU preprocessing per tower, features out) == preprocessing with each
+    tower's processor and calling the towers, bit for bit — single tower and the clip336.dinov2 dual tower."""
+    from law_of_vision_representation_in_mllms_b200 import extract as X
+    from law_of_vision_representation_in_mllms_b200 import specs as S
+    rng = np.random.default_rng(3)
+    imgs = [synth.synthetic_rgb_image(int(h), int(w), 700 + i) for i, (h, w) in enumerate(rng.integers(150, 600, (11, 2)))]
+    for selector in ("openai/clip-vit-large-patch14-336", "openai/clip-vit-large-patch14-336.facebook/dinov2-large"):
+        ex = X.build_extractor(selector, chunk=4, lovr_max_batch=4, lovr_image_size=336,
+                               lovr_spec=None)
+        got = ex.run_images(imgs)
+        torch.cuda.synchronize()
+        parts = []
+        for t in ex.towers:
+            px = t.image_processor.preprocess(imgs, dtype=torch.bfloat16)["pixel_values"]
+            parts.append(torch.cat([t(px[s:s + 4]) for s in range(0, len(imgs), 4)]))
+        want = torch.cat(parts, dim=-1).cpu()
+        assert got.shape == want.shape and torch.equal(got, want), selector
