@@ -459,6 +459,18 @@ int launch_attention(const void* qkv, void* out, int n_img, int T, int H, int im
 int launch_im2col(const void* pixels, int dt, void* cols, int n_img, int R, int P, int Kpad, bool f16, cudaStream_t s) {
   if (n_img <= 0) return 0;
   const int G = R / P;
+  // 16-bit pixels already in the operand format: word-copy kernel (no conversion, constant divisors)
+  const bool same16 = (dt == LOVR_DT_BF16 && !f16) || (dt == LOVR_DT_F16 && f16);
+  if (same16 && (P == 14 || P == 16) && R % 2 == 0 && Kpad % 2 == 0 && (reinterpret_cast<uintptr_t>(pixels) & 3) == 0) {
+    const size_t rows = static_cast<size_t>(n_img) * G * G;
+    const unsigned g16 = static_cast<unsigned>((rows + 7) / 8);
+    if (P == 14)
+      lovr::im2col16_kernel<14><<<g16, 256, 0, s>>>(static_cast<const uint32_t*>(pixels), static_cast<uint32_t*>(cols), n_img, R, G, Kpad);
+    else
+      lovr::im2col16_kernel<16><<<g16, 256, 0, s>>>(static_cast<const uint32_t*>(pixels), static_cast<uint32_t*>(cols), n_img, R, G, Kpad);
+    LAUNCH_CHECK("im2col16_kernel");
+    return 0;
+  }
   const size_t total = static_cast<size_t>(n_img) * G * G * Kpad;
   const unsigned grid = static_cast<unsigned>(std::min<size_t>((total + 255) / 256, 148 * 32));
   lovr::im2col_kernel<<<grid, 256, 0, s>>>(pixels, dt, static_cast<uint16_t*>(cols), n_img, R, P, G, Kpad, f16 ? 1 : 0);

@@ -40,6 +40,32 @@ __global__ void im2col_kernel(const void* __restrict__ pixels, int dt, uint16_t*
   }
 }
 
+// Same gather when the pixels already are in the 16-bit operand format (the extraction path: bf16 in, bf16 operands): pure
+// 32-bit word copies, one warp per patch row, constant divisors.  P even, R even: every P-element source run and every
+// destination word is 4-byte aligned.  The generic kernel above ran at 0.5 TB/s (a div/mod chain per element).
+template <int P>
+__global__ void im2col16_kernel(const uint32_t* __restrict__ pixels, uint32_t* __restrict__ cols, int n_img, int R, int G,
+                                int Kpad) {
+  constexpr int K = 3 * P * P;
+  const int lane = threadIdx.x & 31;
+  const size_t row = blockIdx.x * static_cast<size_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= static_cast<size_t>(n_img) * G * G) return;
+  const int gx = static_cast<int>(row % G);
+  const int gy = static_cast<int>((row / G) % G);
+  const size_t n = row / (static_cast<size_t>(G) * G);
+  uint32_t* dst = cols + row * (Kpad >> 1);
+  for (int w = lane; w < (Kpad >> 1); w += 32) {
+    const int k = 2 * w;
+    uint32_t v = 0u;
+    if (k < K) {
+      const int seg = k / P, off = k - seg * P;       // seg = c * P + py
+      const int c = seg / P, py = seg - c * P;
+      v = __ldg(pixels + ((((n * 3 + c) * R + (gy * P + py)) * static_cast<size_t>(R) + gx * P + off) >> 1));
+    }
+    dst[w] = v;
+  }
+}
+
 // V4 = float4 per lane (D = 128 * V4).  Two-pass statistics on register-resident values.
 template <int V4>
 __device__ __forceinline__ void warp_layernorm(float (&v)[V4 * 4], const float* __restrict__ gamma,

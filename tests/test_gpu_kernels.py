@@ -113,6 +113,10 @@ def test_im2col_matches_unfold(R, P, kpad, dtype):
     want = F.unfold(px.float(), kernel_size=P, stride=P).transpose(1, 2).reshape(-1, 3 * P * P)
     assert torch.equal(cols[:, : 3 * P * P].float(), want.to(torch.bfloat16).float())
     assert cols[:, 3 * P * P:].abs().max().item() == 0 if kpad > 3 * P * P else True
+    if dtype != torch.float32:      # pixels already in the operand format: the word-copy kernel, exact
+        same = G.im2col(px, P, kpad, out_dtype=dtype)
+        assert torch.equal(same[:, : 3 * P * P].float(), want.to(dtype).float())
+        assert kpad == 3 * P * P or same[:, 3 * P * P:].abs().max().item() == 0
 
 
 def _torch_attention(qkv, n, T, H):
