@@ -165,6 +165,86 @@ __global__ void kp_sim_rows_kernel(const T* __restrict__ d1, const T* __restrict
   }
 }
 
+// Same arithmetic, D % 128 == 0: each lane owns 4 consecutive channels per 128-channel chunk, so the target row comes in as
+// 8- or 16-byte loads and the K source rows are read from shared memory as float4 (one LDS.128 per 4 FMAs instead of one
+// LDS.32 per FMA: the scalar version above was shared-memory-issue-bound at 28 us per P = 60 pair, 25x its HBM roofline).
+template <typename T, int NC>  // NC = D / 128 chunks
+__global__ void kp_sim_rows4_kernel(const T* __restrict__ d1, const T* __restrict__ d2, const int* __restrict__ idx, int K,
+                                    int PP, int rows_per_block, float* __restrict__ out) {
+  constexpr int D = NC * 128;
+  extern __shared__ float s1[];  // [K][D]
+  __shared__ float s_inv[kMaxKps];
+  const int b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const T* d1b = d1 + static_cast<size_t>(b) * PP * D;
+  const T* d2b = d2 + static_cast<size_t>(b) * PP * D;
+  auto load4 = [&](const T* p) -> float4 {
+    if constexpr (sizeof(T) == 4) {
+      return __ldg(reinterpret_cast<const float4*>(p));
+    } else {
+      const uint2 w = __ldg(reinterpret_cast<const uint2*>(p));
+      const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.x));
+      const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.y));
+      return make_float4(a.x, a.y, c.x, c.y);
+    }
+  };
+  for (int k = warp; k < K; k += nwarps) {
+    const int r = idx[static_cast<size_t>(b) * K + k];
+    float ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const float4 v = load4(d1b + static_cast<size_t>(r) * D + c * 128 + 4 * lane);
+      *reinterpret_cast<float4*>(&s1[k * D + c * 128 + 4 * lane]) = v;
+      ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    ss = warp_sum(ss);
+    if (lane == 0) s_inv[k] = 1.0f / (sqrtf(ss) + 1e-10f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * D; i += blockDim.x) s1[i] *= s_inv[i / D];
+  __syncthreads();
+  const int t0 = blockIdx.x * rows_per_block;
+  const int t1 = min(PP, t0 + rows_per_block);
+  // two target rows per pass: every float4 of a source row read from shared memory feeds 8 FMAs
+  for (int t = t0 + 2 * warp; t < t1; t += 2 * nwarps) {
+    const bool two = t + 1 < t1;
+    const int tb = two ? t + 1 : t;
+    float4 va[NC], vb[NC];
+    float sa = 0.f, sb = 0.f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      va[c] = load4(d2b + static_cast<size_t>(t) * D + c * 128 + 4 * lane);
+      vb[c] = load4(d2b + static_cast<size_t>(tb) * D + c * 128 + 4 * lane);
+      sa += va[c].x * va[c].x + va[c].y * va[c].y + va[c].z * va[c].z + va[c].w * va[c].w;
+      sb += vb[c].x * vb[c].x + vb[c].y * vb[c].y + vb[c].z * vb[c].z + vb[c].w * vb[c].w;
+    }
+    sa = warp_sum(sa);
+    sb = warp_sum(sb);
+    const float inva = 1.0f / (sqrtf(sa) + 1e-10f), invb = 1.0f / (sqrtf(sb) + 1e-10f);
+    for (int k = 0; k < K; ++k) {
+      float a = 0.f, bsum = 0.f;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const float4 w = *reinterpret_cast<const float4*>(&s1[k * D + c * 128 + 4 * lane]);
+        a = fmaf(va[c].x, w.x, a);
+        a = fmaf(va[c].y, w.y, a);
+        a = fmaf(va[c].z, w.z, a);
+        a = fmaf(va[c].w, w.w, a);
+        bsum = fmaf(vb[c].x, w.x, bsum);
+        bsum = fmaf(vb[c].y, w.y, bsum);
+        bsum = fmaf(vb[c].z, w.z, bsum);
+        bsum = fmaf(vb[c].w, w.w, bsum);
+      }
+      a = warp_sum(a);
+      bsum = warp_sum(bsum);
+      if (lane == 0) {
+        out[(static_cast<size_t>(b) * K + k) * PP + t] = a * inva;
+        if (two) out[(static_cast<size_t>(b) * K + k) * PP + t + 1] = bsum * invb;
+      }
+    }
+  }
+}
+
 // Per-pair PCK (pck_train.py:150-163): fraction of visible keypoints with ||pred-gt|| < alpha*thr,
 // alpha in {0.1, 0.05, 0.01}.  out[b] = {pck@.1, pck@.05, pck@.01, #visible}.
 __global__ void pck_kernel(const float* __restrict__ pred, const float* __restrict__ gt,

@@ -1050,24 +1050,34 @@ int lovr_c_score_keypoints(const void* desc1, const void* desc2, int32_t dtype, 
   const size_t smem = static_cast<size_t>(K) * D * 4;
   const int rpb = 64;
   dim3 grid((PP + rpb - 1) / rpb, static_cast<unsigned>(n_pairs));
-  if (dtype == LOVR_DT_F32) {
-    static size_t set_for = 0;
-    if (smem > set_for) {
-      CUDA_TRY(cudaFuncSetAttribute(kp_sim_rows_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-      set_for = smem;
-    }
-    kp_sim_rows_kernel<float><<<grid, 256, smem, s>>>(static_cast<const float*>(desc1), static_cast<const float*>(desc2),
-                                                      patch_idx, K, PP, D, rpb, rows);
+#define LOVR_KP_LAUNCH(KERN_, ...)                                                                                    \
+  do {                                                                                                               \
+    static size_t set_for = 0;                                                                                       \
+    if (smem > set_for) {                                                                                            \
+      CUDA_TRY(cudaFuncSetAttribute(KERN_, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));    \
+      set_for = smem;                                                                                                \
+    }                                                                                                                \
+    KERN_<<<grid, 256, smem, s>>>(__VA_ARGS__);                                                                      \
+  } while (0)
+  const float* f1 = static_cast<const float*>(desc1);
+  const float* f2 = static_cast<const float*>(desc2);
+  const __nv_bfloat16* h1 = static_cast<const __nv_bfloat16*>(desc1);
+  const __nv_bfloat16* h2 = static_cast<const __nv_bfloat16*>(desc2);
+  const bool f32 = dtype == LOVR_DT_F32;
+  if (D == 1024) {
+    if (f32) LOVR_KP_LAUNCH((kp_sim_rows4_kernel<float, 8>), f1, f2, patch_idx, K, PP, rpb, rows);
+    else LOVR_KP_LAUNCH((kp_sim_rows4_kernel<__nv_bfloat16, 8>), h1, h2, patch_idx, K, PP, rpb, rows);
+  } else if (D == 768) {
+    if (f32) LOVR_KP_LAUNCH((kp_sim_rows4_kernel<float, 6>), f1, f2, patch_idx, K, PP, rpb, rows);
+    else LOVR_KP_LAUNCH((kp_sim_rows4_kernel<__nv_bfloat16, 6>), h1, h2, patch_idx, K, PP, rpb, rows);
+  } else if (D == 2048) {
+    if (f32) LOVR_KP_LAUNCH((kp_sim_rows4_kernel<float, 16>), f1, f2, patch_idx, K, PP, rpb, rows);
+    else LOVR_KP_LAUNCH((kp_sim_rows4_kernel<__nv_bfloat16, 16>), h1, h2, patch_idx, K, PP, rpb, rows);
   } else {
-    static size_t set_for = 0;
-    if (smem > set_for) {
-      CUDA_TRY(cudaFuncSetAttribute(kp_sim_rows_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-      set_for = smem;
-    }
-    kp_sim_rows_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>(static_cast<const __nv_bfloat16*>(desc1),
-                                                              static_cast<const __nv_bfloat16*>(desc2), patch_idx, K, PP, D,
-                                                              rpb, rows);
+    if (f32) LOVR_KP_LAUNCH(kp_sim_rows_kernel<float>, f1, f2, patch_idx, K, PP, D, rpb, rows);
+    else LOVR_KP_LAUNCH(kp_sim_rows_kernel<__nv_bfloat16>, h1, h2, patch_idx, K, PP, D, rpb, rows);
   }
+#undef LOVR_KP_LAUNCH
   LAUNCH_CHECK("kp_sim_rows_kernel");
   return launch_flow_rows(rows, PP, static_cast<size_t>(n_pairs) * K, P, window, soft, anno_size / P, kps_out, nullptr, s);
 }
