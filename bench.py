@@ -393,7 +393,7 @@ def main():
         )
         if a_info:
             line["a_score"] = a_info
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # reported on rank 0 at N=1 only
             cpu_reference_leg(1)
             v, dt, thr = cpu_reference_leg(args.cpu_images)
             line["cpu_baseline"] = dict(value=v, unit="images/s", cores=thr, kind="port",
