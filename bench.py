@@ -153,8 +153,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="images per step per GPU")
-    ap.add_argument("--chunk", type=int, default=128, help="images per native tower call")
+    ap.add_argument("--batch", type=int, default=512, help="images per step per GPU")
+    ap.add_argument("--chunk", type=int, default=256, help="images per native tower call (256: +2 % over 128, measured)")
     ap.add_argument("--cpu-images", type=int, default=32, help="images per CPU-baseline sample / reference-arm step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-a-score", action="store_true")
@@ -386,9 +386,10 @@ def main():
             roofline=dict(bound="tensor", kernel="gemm_tcgen05_kernel (all dense layers)", achieved=achieved,
                           peak=peaks["tflops"], unit="TFLOP/s", frac=achieved / peaks["tflops"], peak_source=peaks["source"],
                           launches=gemm_launches, gemm_share_of_step=gemm_ms / ms,
-                          traffic=(807e6 if args.chunk == 128 else None),
-                          traffic_note="avg DRAM read+write bytes per dense-layer GEMM launch at 128 images (ncu --set full, "
-                                       "profiles/r01_ncu_summary_final.md)",
+                          traffic=807e6 * args.chunk / 128,
+                          traffic_note="avg DRAM read+write bytes per dense-layer GEMM launch: 807 MB measured at 128 images per "
+                                       "launch (ncu --set full, profiles/r01_ncu_summary_final.md), scaled to this chunk "
+                                       "(every term is proportional to the row count; weights are 0.3 % of it)",
                           whole_step_tflops=value / world * FLOPS_PER_IMAGE / 1e12),
         )
         if a_info:
