@@ -166,6 +166,11 @@ int lovr_c_score_keypoints(const void* desc1, const void* desc2, int32_t dtype, 
 size_t lovr_c_score_mutual_nn_workspace_bytes(int32_t dtype, int64_t n_pairs, int32_t P, int32_t D);
 int lovr_c_score_mutual_nn(const void* desc1, const void* desc2, int32_t dtype, int64_t n_pairs, int32_t P, int32_t D,
                            float* out /* [n_pairs, 2] */, void* workspace, size_t workspace_bytes, void* stream);
+/* Two-model descriptors (C_score/pck_train_two.py:24-35): out[r, :] = [ n(a[r, :]) , n(b[r, :]) ], n(x) = x / (||x|| + 1e-10);
+ * a [rows, Da], b [rows, Db], out [rows, Da + Db], all `dtype` (bf16 or fp32).  The renormalisation of the concatenation
+ * that follows in the reference is fused into the similarity kernels above. */
+int lovr_c_score_concat_two(const void* a, const void* b, int32_t dtype, int64_t rows, int32_t Da, int32_t Db, void* out,
+                            void* stream);
 int lovr_pck(const float* pred, const float* gt, const uint8_t* visible, const float* thresholds, int64_t n_pairs,
              int32_t K, float* out, void* stream);
 

@@ -26,7 +26,7 @@ EXPORTS = [
     "lovr_gemm_bf16", "lovr_layernorm_bf16", "lovr_attention", "lovr_im2col",
     "lovr_a_score_workspace_bytes", "lovr_a_score_maxcos",
     "lovr_c_score_workspace_bytes", "lovr_c_score_flow", "lovr_c_score_keypoints", "lovr_pck",
-    "lovr_c_score_mutual_nn_workspace_bytes", "lovr_c_score_mutual_nn",
+    "lovr_c_score_mutual_nn_workspace_bytes", "lovr_c_score_mutual_nn", "lovr_c_score_concat_two",
     "lovr_cka_workspace_bytes", "lovr_cka_gram_elems", "lovr_cka_accumulate", "lovr_cka_finalize",
     "lovr_preprocess_workspace_bytes", "lovr_preprocess",
 ]
@@ -109,6 +109,8 @@ def lib():
     L.lovr_c_score_mutual_nn_workspace_bytes.argtypes = [i32, i64, i32, i32]
     L.lovr_c_score_mutual_nn.restype = C.c_int
     L.lovr_c_score_mutual_nn.argtypes = [vp, vp, i32, i64, i32, i32, vp, vp, sz, vp]
+    L.lovr_c_score_concat_two.restype = C.c_int
+    L.lovr_c_score_concat_two.argtypes = [vp, vp, i32, i64, i32, i32, vp, vp]
     L.lovr_pck.restype = C.c_int
     L.lovr_pck.argtypes = [vp, vp, vp, vp, i64, i32, vp, vp]
     L.lovr_cka_workspace_bytes.restype = sz

@@ -28,12 +28,24 @@ def desc_from_feature_map(fmap):
     return fmap.reshape(1, 1, fmap.shape[1], -1).permute(0, 1, 3, 2)[0]
 
 
-def concat_two_models(desc_a, desc_b, eps=1e-10):
-    """pck_train_two.py:24-35 — normalise each model's descriptors, concatenate channels (the fused kernels then
-    renormalise).  Tiny per-token arithmetic on [B,P*P,C]; kept in torch as data preparation."""
-    na = desc_a / (torch.linalg.norm(desc_a, dim=-1, keepdim=True) + eps)
-    nb = desc_b / (torch.linalg.norm(desc_b, dim=-1, keepdim=True) + eps)
-    return torch.cat([na, nb], dim=-1)
+def concat_two_models(desc_a, desc_b):
+    """pck_train_two.py:24-35 — normalise each model's descriptors and concatenate the channels (`lovr_c_score_concat_two`);
+    the renormalisation of the concatenation is fused into the similarity kernels.  desc [B,P*P,C1], [B,P*P,C2] on the
+    device, same dtype (fp32 or bf16) -> [B,P*P,C1+C2]."""
+    if desc_a.shape[:-1] != desc_b.shape[:-1]:
+        raise ValueError(f"descriptor grids differ: {tuple(desc_a.shape)} vs {tuple(desc_b.shape)}")
+    if not desc_a.is_cuda:
+        raise _lib.LovrError("C-score kernels need CUDA tensors: this package has no CPU path")
+    if desc_a.dtype not in (torch.float32, torch.bfloat16):
+        desc_a = desc_a.float()
+    a, b = desc_a.contiguous(), desc_b.to(desc_a.dtype).contiguous()
+    out = torch.empty(*a.shape[:-1], a.shape[-1] + b.shape[-1], dtype=a.dtype, device=a.device)
+    rows = a.numel() // a.shape[-1]
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.lib().lovr_c_score_concat_two(_lib.ptr(a), _lib.ptr(b), _lib.torch_dtype_code(a.dtype), rows,
+                                                      a.shape[-1], b.shape[-1], _lib.ptr(out), _lib.stream_ptr(a.device)),
+                   "lovr_c_score_concat_two")
+    return out
 
 
 def kpts_to_patch_idx(kps, num_patches, anno_size=ANNO_SIZE):

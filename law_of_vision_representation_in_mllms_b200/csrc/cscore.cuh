@@ -245,6 +245,35 @@ __global__ void kp_sim_rows4_kernel(const T* __restrict__ d1, const T* __restric
   }
 }
 
+// Two-model descriptors (C_score/pck_train_two.py:24-35, the DUMMY_NET branch): out[r] = [ a[r] / (|a[r]| + 1e-10) , b[r] / (|b[r]| + 1e-10) ];
+// the final renormalisation of that file is the one the similarity kernels fuse.  One warp per row, fp32 arithmetic.
+template <typename T>
+__global__ void concat_normalize_kernel(const T* __restrict__ a, const T* __restrict__ b, size_t rows, int Da, int Db,
+                                        T* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const size_t row = blockIdx.x * static_cast<size_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const T* src[2] = {a + row * Da, b + row * Db};
+  const int dim[2] = {Da, Db};
+  T* dst = out + row * (static_cast<size_t>(Da) + Db);
+#pragma unroll
+  for (int m = 0; m < 2; ++m) {
+    float ss = 0.f;
+    for (int e = lane; e < dim[m]; e += 32) {
+      const float v = to_f32<T>(src[m][e]);
+      ss += v * v;
+    }
+    ss = warp_sum(ss);
+    const float nrm = sqrtf(ss) + 1e-10f;
+    for (int e = lane; e < dim[m]; e += 32) {
+      const float v = to_f32<T>(src[m][e]) / nrm;
+      if constexpr (sizeof(T) == 4) dst[e] = v;
+      else dst[e] = __float2bfloat16(v);
+    }
+    dst += dim[m];
+  }
+}
+
 // Per-pair PCK (pck_train.py:150-163): fraction of visible keypoints with ||pred-gt|| < alpha*thr,
 // alpha in {0.1, 0.05, 0.01}.  out[b] = {pck@.1, pck@.05, pck@.01, #visible}.
 __global__ void pck_kernel(const float* __restrict__ pred, const float* __restrict__ gt,

@@ -1082,6 +1082,25 @@ int lovr_c_score_keypoints(const void* desc1, const void* desc2, int32_t dtype, 
   return launch_flow_rows(rows, PP, static_cast<size_t>(n_pairs) * K, P, window, soft, anno_size / P, kps_out, nullptr, s);
 }
 
+int lovr_c_score_concat_two(const void* a, const void* b, int32_t dtype, int64_t rows, int32_t Da, int32_t Db, void* out,
+                            void* stream) {
+  if (int rc = require_device()) return rc;
+  if (!a || !b || !out) return fail(LOVR_E_ARG, "c_score_concat_two: null pointer");
+  if (dtype != LOVR_DT_BF16 && dtype != LOVR_DT_F32) return fail(LOVR_E_UNSUPPORTED, "c_score_concat_two: dtype %d (bf16 or fp32)", dtype);
+  if (rows <= 0 || Da <= 0 || Db <= 0) return fail(LOVR_E_ARG, "c_score_concat_two: sizes must be positive");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
+  if (dtype == LOVR_DT_F32)
+    lovr::concat_normalize_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(a), static_cast<const float*>(b),
+                                                              static_cast<size_t>(rows), Da, Db, static_cast<float*>(out));
+  else
+    lovr::concat_normalize_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(
+        static_cast<const __nv_bfloat16*>(a), static_cast<const __nv_bfloat16*>(b), static_cast<size_t>(rows), Da, Db,
+        static_cast<__nv_bfloat16*>(out));
+  LAUNCH_CHECK("concat_normalize_kernel");
+  return 0;
+}
+
 int lovr_pck(const float* pred, const float* gt, const uint8_t* visible, const float* thresholds, int64_t n_pairs,
              int32_t K, float* out, void* stream) {
   if (int rc = require_device()) return rc;

@@ -3,6 +3,7 @@
 SURVEY.md App. D: apply it relative — fp32 ulp at ~800 px is 6e-5), i.e. |dx| <= 1e-5 * 840 px, and exact PCK."""
 import os
 
+import numpy as np
 import pytest
 import torch
 
@@ -133,3 +134,32 @@ def test_mutual_nn_batch_counts_and_dtypes():
             want, n = co.mutual_nn_distance(co.normalize_feats(a[i:i + 1].float()), co.normalize_feats(b[i:i + 1].float()))
             assert int(cnt[i]) == n, (i, int(cnt[i]), n)
             assert abs(float(dist[i]) - want) < tol, (i, float(dist[i]) - want)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_two_model_concat_matches_pck_train_two(dtype):
+    """pck_train_two.py:24-35: per-model normalisation, channel concat, renormalisation (fused downstream) — against the
+    oracle restatement, through the keypoint transformation the reference applies next."""
+    g = torch.Generator().manual_seed(9)
+    P, K = 24, 10
+    a = torch.randn(2, P * P, 1024, generator=g) * 3.0
+    b = torch.randn(2, P * P, 768, generator=g) * 0.2          # models with very different feature scales
+    a2 = 0.6 * torch.roll(a, 5, dims=1) + 0.4 * torch.randn(2, P * P, 1024, generator=g) * 3.0
+    b2 = 0.6 * torch.roll(b, 5, dims=1) + 0.4 * torch.randn(2, P * P, 768, generator=g) * 0.2
+    a, b, a2, b2 = (t.to(dtype) for t in (a, b, a2, b2))
+    d1 = CS.concat_two_models(a.cuda(), b.cuda())
+    d2 = CS.concat_two_models(a2.cuda(), b2.cuda())
+    cat = torch.cat([co.normalize_feats(a.float()), co.normalize_feats(b.float())], dim=-1)
+    tol = 1e-6 if dtype == torch.float32 else 4e-3
+    assert d1.dtype == dtype and (d1.float().cpu() - cat).abs().max() < tol
+    kps = torch.rand(K, 3, generator=g) * 839.0
+    idx = CS.kpts_to_patch_idx(kps, P)
+    got = CS.keypoint_transformation(d1, d2, np.stack([idx, idx]), soft=True, window=5).cpu()
+    for i in range(2):
+        n1 = co.normalize_feats(d1[i:i + 1].float().cpu())       # the oracle sees the same (possibly bf16-rounded) concat
+        n2 = co.normalize_feats(d2[i:i + 1].float().cpu())
+        want = co.keypoint_transformation(n1, n2, idx, P, soft=True, window=5)
+        assert (got[i] - want).abs().max() < PIX_TOL
+    if dtype == torch.float32:                                    # and the reference's own normalize_feats of both models
+        want2 = co.normalize_two(a[:1], b[:1])
+        assert (co.normalize_feats(d1[:1].cpu()) - want2).abs().max() < 1e-6
