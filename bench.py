@@ -304,7 +304,7 @@ def main():
         import numpy as np
         from law_of_vision_representation_in_mllms_b200 import preprocess as PP
         rng = np.random.default_rng(rank)
-        raw = [rng.integers(0, 256, (480, 640, 3), dtype=np.uint8) for _ in range(8)] * 32
+        raw = [rng.integers(0, 256, (480, 640, 3), dtype=np.uint8) for _ in range(8)] * (B // 8)   # one step's worth
         host_raw, offs, hw = PP.pack_images(raw)
         dev_raw = host_raw.to(dev)
         pcfg = tower.image_processor._cfg()
@@ -320,7 +320,7 @@ def main():
         barrier()
         pre_ms = e0.elapsed_time(e1) / 5
         a_info["preprocess"] = dict(
-            config="256 x 480x640 8-bit RGB -> CLIP-336 pixels on the device (Pillow-exact bicubic, centre crop, HF normalise), per GPU",
+            config=f"{B} x 480x640 8-bit RGB -> CLIP-336 pixels on the device (Pillow-exact bicubic, centre crop, HF normalise), per GPU",
             images_per_s=len(raw) / pre_ms * 1e3, hbm_gbs=(host_raw.numel() + pout.numel() * 2) / pre_ms / 1e6)
         del dev_raw, pws, pout
         # the same end-to-end path as `e2e`, but from raw 8-bit images: host packing + H2D of bytes + GPU preprocessing +
@@ -337,7 +337,7 @@ def main():
         if world > 1:
             dist.all_reduce(raw_ms, op=dist.ReduceOp.MAX)
         a_info["e2e_from_raw_images"] = dict(
-            api="extract.FeatureExtractor.run_images (256 x 480x640 8-bit RGB on the host -> features on the host)",
+            api=f"extract.FeatureExtractor.run_images ({B} x 480x640 8-bit RGB on the host -> features on the host)",
             images_per_s=world * len(raw) / raw_ms.item() * 1e3, h2d_bytes_per_step=int(host_raw.numel()),
             host_wall_ms_per_step=(time.perf_counter() - t_raw) * 1e3 / 3)
         ex2 = X.build_extractor("openai/clip-vit-large-patch14-336.facebook/dinov2-large", chunk=args.chunk,
