@@ -32,7 +32,7 @@ def to_c_score_layout(features, h, w):
 class FeatureExtractor:
     """Runs one tower (or a dual-tower ModuleList) over host-resident pixel tensors."""
 
-    def __init__(self, vision_tower, chunk=64, out_dtype=None):
+    def __init__(self, vision_tower, chunk=128, out_dtype=None):
         self.tower = vision_tower
         self.towers = list(vision_tower) if isinstance(vision_tower, torch.nn.ModuleList) else [vision_tower]
         self.device = self.towers[0].device
@@ -159,7 +159,7 @@ class FeatureExtractor:
         return host_out
 
 
-def build_extractor(selector, select_layer=-2, select_feature="patch", chunk=64, **tower_args):
+def build_extractor(selector, select_layer=-2, select_feature="patch", chunk=128, **tower_args):
     """`--vision_tower` string -> towers (llava_arch.py grammar) -> FeatureExtractor."""
     import types
     cfg = types.SimpleNamespace(mm_vision_tower=selector, mm_vision_select_layer=select_layer,

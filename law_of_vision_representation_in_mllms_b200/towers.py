@@ -28,7 +28,7 @@ from . import _lib
 from .specs import (FAMILY_CLIP, FAMILY_DINOV2, FAMILY_SIGLIP, TOWER_SPECS, TowerSpec, layers_to_run)
 from .weights import canonical_weights, synthetic_state_dict
 
-DEFAULT_MAX_BATCH = int(os.environ.get("LOVR_MAX_BATCH", "64"))
+DEFAULT_MAX_BATCH = int(os.environ.get("LOVR_MAX_BATCH", "128"))   # images per native call; 8.3 MB of workspace each at ViT-L/336
 
 
 class _NativeTower:
