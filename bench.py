@@ -12,6 +12,7 @@ Under torchrun every rank runs its own shard of images (weak scaling, no data-pa
 CUDA events between barriers, max over ranks.  One JSON line on rank 0.
 """
 import argparse
+import contextlib
 import json
 import os
 import subprocess
@@ -147,6 +148,28 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+@contextlib.contextmanager
+def _stdout_to_stderr():
+    """Point file descriptor 1 at stderr for the duration of the block (C-level prints included); no-op if that fails."""
+    saved = None
+    try:
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+    except OSError:
+        saved = None
+    try:
+        yield
+    finally:
+        if saved is not None:
+            try:
+                sys.stdout.flush()
+                os.dup2(saved, 1)
+                os.close(saved)
+            except OSError:
+                pass
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -178,7 +201,13 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL can print its version banner on stdout from C (seen at 4 ranks): stdout is reserved for the one JSON line, so
+        # communicator creation and the first collective run with fd 1 pointed at stderr.
+        with _stdout_to_stderr():
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
 
     def barrier():
         if world > 1:
