@@ -62,3 +62,14 @@ def test_processor_configurations_follow_the_checkpoints():
     cfg = clip._cfg(pad_square=True)
     assert (cfg.resize_mode, cfg.resize_size, cfg.crop_size, cfg.pad_square) == (0, 336, 336, 1)
     assert list(cfg.pad_rgb)[:3] == [int(m * 255) for m in PP.OPENAI_CLIP_MEAN]      # mm_utils.py:84
+
+
+def test_pil_inputs_are_converted_to_rgb_like_do_convert_rgb():
+    from PIL import Image
+    gray = Image.fromarray(np.arange(48, dtype=np.uint8).reshape(6, 8), mode="L")
+    rgba = Image.fromarray(np.full((4, 5, 4), 200, np.uint8), mode="RGBA")
+    host, offsets, hw = PP.pack_images([gray, rgba])
+    assert hw.tolist() == [[6, 8], [4, 5]] and host.numel() == 6 * 8 * 3 + 4 * 5 * 3
+    g = host.numpy()[: 6 * 8 * 3].reshape(6, 8, 3)
+    assert np.array_equal(g, np.asarray(gray.convert("RGB")))
+    assert np.array_equal(host.numpy()[6 * 8 * 3:].reshape(4, 5, 3), np.asarray(rgba.convert("RGB")))
