@@ -124,6 +124,23 @@ def cpu_reference_leg(n_images):
     return n_images / dt, dt, c["threads"]
 
 
+def cpu_score_leg(threads, n_pairs=12):
+    """A_score/compute.py's per-pair arithmetic as the reference executes it (broadcast F.cosine_similarity over [x,1,D] x
+    [1,y,D], `a_pair_literal`) on a bounded sample of C3-shaped fp32 pairs; -> pairs/s and the extrapolated C3 seconds."""
+    import torch
+    from oracle import a_score_oracle
+    g = torch.Generator().manual_seed(11)
+    o = torch.randn(n_pairs, T_PATCH, D, generator=g)
+    r = 0.5 * o + torch.randn(n_pairs, T_PATCH, D, generator=g)
+    a_score_oracle.a_pair_literal(o[0], r[0])
+    t0 = time.perf_counter()
+    for i in range(n_pairs):
+        a_score_oracle.a_pair_literal(o[i], r[i])
+    dt = time.perf_counter() - t0
+    return dict(kind="port", cores=threads, sample=f"{n_pairs} fp32 pairs of 576 x 576 x 1024, literal compute.py arithmetic, {dt:.1f} s",
+                a_score_pairs_per_s=n_pairs / dt, a_score_c3_seconds_extrapolated=10000 * dt / n_pairs)
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -426,6 +443,11 @@ def main():
         if not args.no_cpu_baseline and world == 1:      # reported on rank 0 at N=1 only
             cpu_reference_leg(1)
             v, dt, thr = cpu_reference_leg(args.cpu_images)
+            if a_info is not None:
+                try:      # the score scripts' arithmetic on the same host cores, bounded sample, reported beside the GPU seconds
+                    a_info["cpu_port"] = cpu_score_leg(thr)
+                except Exception as ex:      # a reported extra, never a reason to lose the bench line
+                    a_info["cpu_port"] = dict(error=str(ex)[:200])
             line["cpu_baseline"] = dict(value=v, unit="images/s", cores=thr, kind="port",
                                         sample=f"{args.cpu_images} synthetic 336px images, fp32 oracle restatement of the "
                                                f"HF CLIP forward, {dt:.1f} s on {thr} threads (calibrated best of "
