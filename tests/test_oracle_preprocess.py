@@ -69,3 +69,33 @@ def test_workspace_query_and_validation_need_no_gpu():
     assert L.lovr_preprocess_workspace_bytes(C.byref(_cfg(mode=7)), 2, hw_p) == 0
     bad = np.array([[0, 10]], dtype=np.int32)
     assert L.lovr_preprocess_workspace_bytes(C.byref(_cfg()), 1, bad.ctypes.data_as(C.POINTER(C.c_int32))) == 0
+
+
+def test_oracle_matches_pillow_property_based():
+    """Hypothesis-driven sizes (incl. 1-pixel sides, identity, extreme aspect ratios): restatement == Pillow, bit for bit."""
+    Image = pytest.importorskip("PIL.Image")
+    hyp = pytest.importorskip("hypothesis")
+    st = pytest.importorskip("hypothesis.strategies")
+
+    @hyp.settings(max_examples=40, deadline=None, derandomize=True)
+    @hyp.given(st.integers(1, 260), st.integers(1, 260), st.integers(1, 200), st.integers(1, 200), st.integers(0, 2 ** 31 - 1))
+    def check(h, w, nh, nw, seed):
+        img = np.random.default_rng(seed).integers(0, 256, (h, w, 3), dtype=np.uint8)
+        want = np.array(Image.fromarray(img).resize((nw, nh), resample=Image.BICUBIC))
+        assert np.array_equal(O.pil_bicubic_resize(img, nw, nh), want), (h, w, nh, nw)
+
+    check()
+
+
+def test_hf_pipeline_restated_against_transformers_pil_backend():
+    """The whole processor pipeline (shortest-edge resize, centre crop, rescale, normalise) against transformers' own
+    PIL-backend CLIP processor — the descendant of the 4.31 slow processor the reference pins."""
+    Image = pytest.importorskip("PIL.Image")
+    mod = pytest.importorskip("transformers.models.clip.image_processing_pil_clip")
+    proc = mod.CLIPImageProcessorPil(size={"shortest_edge": 224}, crop_size={"height": 224, "width": 224})
+    rng = np.random.default_rng(2)
+    for h, w in ((300, 450), (512, 230), (224, 224), (100, 90)):
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        want = proc.preprocess(Image.fromarray(img), return_tensors="np")["pixel_values"][0]
+        got = O.hf_preprocess(img, 224, 224, proc.image_mean, proc.image_std)
+        assert np.array_equal(want, got), (h, w)
