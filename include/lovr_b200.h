@@ -178,8 +178,9 @@ int lovr_pck(const float* pred, const float* gt, const uint8_t* visible, const f
  * Linear CKA (the metric BASELINE.json north_star names; ABSENT from the reference — builder-defined, parity pinned only
  * to the fp64 restatement in oracle/a_score_oracle.py:linear_cka).  X [rows, Dx], Y [rows, Dy] bf16, rows = all
  * N*P tokens.  lovr_cka_accumulate ADDS this shard's uncentred sums into `gram` (fp64, lovr_cka_gram_elems(Dx,Dy)
- * elements: X^T[X|Y] [Dx, Dx+Dy], Y^T Y [Dy, Dy], column sums [Dx+Dy]; zero it first) — that buffer is what the
- * single all-reduce of the multi-GPU path sums over ranks.  lovr_cka_finalize applies the centring G - s s^T / n and
+ * elements: X^T[X|Y] [Dx, Dx+Dy], Y^T Y [Dy, Dy], column sums [Dx+Dy], row count [1]; zero it first) — that ONE buffer
+ * is what the single all-reduce of the multi-GPU path sums over ranks (the row count rides in its last element).
+ * lovr_cka_finalize applies the centring G - s s^T / n (n = n_rows if > 0, else the count in the buffer) and
  * returns out3 = {||Xc^T Yc||_F^2, ||Xc^T Xc||_F^2, ||Yc^T Yc||_F^2};  CKA = out3[0] / sqrt(out3[1]*out3[2]).
  * ------------------------------------------------------------------------------------------------- */
 size_t lovr_cka_workspace_bytes(int64_t rows, int32_t Dx, int32_t Dy);

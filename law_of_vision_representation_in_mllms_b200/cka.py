@@ -3,8 +3,8 @@ see SURVEY.md §0 F1 — so this is builder-defined and pinned only to the fp64 
 
     CKA(X, Y) = ||Yc^T Xc||_F^2 / (||Xc^T Xc||_F ||Yc^T Yc||_F),   Xc = X - mean_rows(X),  rows = all N*P tokens
 
-`cka_gram` accumulates the uncentred fp64 sums of one shard (rows may be processed in slabs); the multi-GPU path
-all-reduces that one buffer (distributed.all_reduce_sum) and calls `cka_from_gram`.
+`cka_gram` accumulates the uncentred fp64 sums of one shard (rows may be processed in slabs) and the shard's row count
+into ONE buffer; the multi-GPU path all-reduces that buffer once (distributed.cka_reduce) and calls `cka_from_gram`.
 """
 import ctypes as C
 
@@ -54,9 +54,10 @@ def cka_gram(X, Y, gram=None):
 
 
 def cka_from_gram(gram, n_rows, Dx, Dy):
+    """n_rows None -> the row count accumulated in the buffer's last element (what the multi-GPU path all-reduces)."""
     out = torch.empty(3, dtype=torch.float64, device=gram.device)
     with torch.cuda.device(gram.device):
-        _lib.check(_lib.lib().lovr_cka_finalize(_lib.ptr(gram), float(n_rows), Dx, Dy, _lib.ptr(out),
+        _lib.check(_lib.lib().lovr_cka_finalize(_lib.ptr(gram), float(n_rows) if n_rows else 0.0, Dx, Dy, _lib.ptr(out),
                                                 _lib.stream_ptr(gram.device)), "lovr_cka_finalize")
     xy, xx, yy = out.cpu().tolist()
     return xy / (xx * yy) ** 0.5

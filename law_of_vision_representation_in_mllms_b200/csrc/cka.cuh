@@ -52,9 +52,11 @@ transpose_colsum_kernel(const uint16_t* __restrict__ X, size_t R, int D, uint16_
 }
 
 // out[i] (fp64) += sum_b partial[b * stride + i]; the accumulate form lets several calls (shards) add up.
+// count (optional): *count += add_rows, by one thread — the shard's row count rides in the Gram buffer.
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, size_t stride, int splits, size_t n,
-                                       double* __restrict__ out) {
+                                       double* __restrict__ out, double* __restrict__ count, double add_rows) {
   const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i == 0 && count != nullptr) *count += add_rows;
   if (i >= n) return;
   double s = 0.0;
   for (int b = 0; b < splits; ++b) s += static_cast<double>(partial[static_cast<size_t>(b) * stride + i]);
@@ -65,8 +67,10 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, size_t
 // out[0] = ||Xc^T Yc||_F^2, out[1] = ||Xc^T Xc||_F^2, out[2] = ||Yc^T Yc||_F^2 with the centring applied as
 // G - s s^T / n.
 __global__ void cka_finalize_kernel(const double* __restrict__ Ga, const double* __restrict__ Gb,
-                                    const double* __restrict__ s, double n, int Dx, int Dy, double* __restrict__ out) {
+                                    const double* __restrict__ s, double n_arg, const double* __restrict__ n_buf, int Dx,
+                                    int Dy, double* __restrict__ out) {
   __shared__ double part[3][32];
+  const double n = n_arg > 0.0 ? n_arg : *n_buf;
   const int Dz = Dx + Dy;
   const size_t na = static_cast<size_t>(Dx) * Dz, nb = static_cast<size_t>(Dy) * Dy;
   double a_xy = 0, a_xx = 0, a_yy = 0;

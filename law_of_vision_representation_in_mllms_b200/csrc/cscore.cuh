@@ -104,7 +104,8 @@ __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return
 // grid (ceil(PP / rows_per_block), n_pairs); smem: K normalised source rows (K*D floats).
 template <typename T>
 __global__ void kp_sim_rows_kernel(const T* __restrict__ d1, const T* __restrict__ d2, const int* __restrict__ idx,
-                                   int K, int PP, int D, int rows_per_block, float* __restrict__ out) {
+                                   int Kall, int k0, int K, int PP, int D, int rows_per_block, float* __restrict__ out) {
+  // keypoints [k0, k0 + K) of the pair's Kall: the host splits K so that K * D floats fit in shared memory
   extern __shared__ float s1[];  // [K][D]
   __shared__ float s_inv[kMaxKps];
   const int b = blockIdx.y;
@@ -112,7 +113,7 @@ __global__ void kp_sim_rows_kernel(const T* __restrict__ d1, const T* __restrict
   const T* d1b = d1 + static_cast<size_t>(b) * PP * D;
   const T* d2b = d2 + static_cast<size_t>(b) * PP * D;
   for (int k = warp; k < K; k += nwarps) {
-    const int r = idx[static_cast<size_t>(b) * K + k];
+    const int r = idx[static_cast<size_t>(b) * Kall + k0 + k];
     float ss = 0.f;
     for (int e = lane; e < D; e += 32) {
       const float v = to_f32<T>(d1b[static_cast<size_t>(r) * D + e]);
@@ -159,7 +160,7 @@ __global__ void kp_sim_rows_kernel(const T* __restrict__ d1, const T* __restrict
     for (int k = 0; k < kMaxKps; ++k) {
       if (k < K) {
         const float d = warp_sum(dots[k]);
-        if (lane == 0) out[(static_cast<size_t>(b) * K + k) * PP + t] = d * inv2;
+        if (lane == 0) out[(static_cast<size_t>(b) * Kall + k0 + k) * PP + t] = d * inv2;
       }
     }
   }
@@ -169,8 +170,8 @@ __global__ void kp_sim_rows_kernel(const T* __restrict__ d1, const T* __restrict
 // 8- or 16-byte loads and the K source rows are read from shared memory as float4 (one LDS.128 per 4 FMAs instead of one
 // LDS.32 per FMA: the scalar version above was shared-memory-issue-bound at 28 us per P = 60 pair, 25x its HBM roofline).
 template <typename T, int NC>  // NC = D / 128 chunks
-__global__ void kp_sim_rows4_kernel(const T* __restrict__ d1, const T* __restrict__ d2, const int* __restrict__ idx, int K,
-                                    int PP, int rows_per_block, float* __restrict__ out) {
+__global__ void kp_sim_rows4_kernel(const T* __restrict__ d1, const T* __restrict__ d2, const int* __restrict__ idx, int Kall,
+                                    int k0, int K, int PP, int rows_per_block, float* __restrict__ out) {
   constexpr int D = NC * 128;
   extern __shared__ float s1[];  // [K][D]
   __shared__ float s_inv[kMaxKps];
@@ -189,7 +190,7 @@ __global__ void kp_sim_rows4_kernel(const T* __restrict__ d1, const T* __restric
     }
   };
   for (int k = warp; k < K; k += nwarps) {
-    const int r = idx[static_cast<size_t>(b) * K + k];
+    const int r = idx[static_cast<size_t>(b) * Kall + k0 + k];
     float ss = 0.f;
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
@@ -238,8 +239,8 @@ __global__ void kp_sim_rows4_kernel(const T* __restrict__ d1, const T* __restric
       a = warp_sum(a);
       bsum = warp_sum(bsum);
       if (lane == 0) {
-        out[(static_cast<size_t>(b) * K + k) * PP + t] = a * inva;
-        if (two) out[(static_cast<size_t>(b) * K + k) * PP + t + 1] = bsum * invb;
+        out[(static_cast<size_t>(b) * Kall + k0 + k) * PP + t] = a * inva;
+        if (two) out[(static_cast<size_t>(b) * Kall + k0 + k) * PP + t + 1] = bsum * invb;
       }
     }
   }

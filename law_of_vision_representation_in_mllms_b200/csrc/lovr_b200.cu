@@ -96,6 +96,22 @@ int require_device() {
   return 0;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute of a kernel: remember the largest value set for
+// (device, kernel) under a mutex, so several GPUs in one process and several host threads both work.
+int ensure_smem(const void* func, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, size_t> set;
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> g(mu);
+  size_t& cur = set[std::make_pair(dev, func)];
+  if (bytes > cur) {
+    CUDA_TRY(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+    cur = bytes;
+  }
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------ tensor maps
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -178,12 +194,8 @@ template <int BN, int EPI, int ACT, bool F16>
 int launch_gemm_inst(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const lovr::GemmArgs& args,
                      cudaStream_t s) {
   auto kern = lovr::gemm_tcgen05_kernel<BN, EPI, ACT, F16>;
-  static bool attr_set = false;
   const int smem = lovr::GemmSmem<BN>::kTotal;
-  if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  if (int rc = ensure_smem(reinterpret_cast<const void*>(kern), smem)) return rc;
   const int m_tiles = (args.M + lovr::kBM - 1) / lovr::kBM;
   const int n_tiles = (args.N + BN - 1) / BN;
   const int units = args.batch * m_tiles * (n_tiles / args.n_inner);
@@ -224,12 +236,8 @@ template <int EPI, int ACT, bool F16, int EW>
 int launch_gemm2_inst(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const lovr::GemmArgs& args,
                       cudaStream_t s) {
   auto kern = lovr::gemm2_tcgen05_kernel<EPI, ACT, F16, EW>;
-  static bool attr_set = false;
   const int smem = lovr::Gemm2Smem<EPI, EW>::kTotal;
-  if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  if (int rc = ensure_smem(reinterpret_cast<const void*>(kern), smem)) return rc;
   const int units = ((args.M + 255) / 256) * (args.N / 256);
   int grid = 2 * units < device_info().sms ? 2 * units : (device_info().sms & ~1);
   if (grid <= 0) return 0;
@@ -333,14 +341,8 @@ int launch_attention(const void* qkv, void* out, int n_img, int T, int H, int im
   const int D = H * 64;
   if (impl == LOVR_ATTN_SIMT_CHECK) {
     const size_t smem = lovr::attn_simt_smem_bytes(T);
-    static size_t set_for = 0;
-    if (smem > set_for) {
-      CUDA_TRY(cudaFuncSetAttribute(lovr::attention_simt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    static_cast<int>(smem)));
-      CUDA_TRY(cudaFuncSetAttribute(lovr::attention_simt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    static_cast<int>(smem)));
-      set_for = smem;
-    }
+    if (int rc = ensure_smem(reinterpret_cast<const void*>(lovr::attention_simt_kernel<true>), smem)) return rc;
+    if (int rc = ensure_smem(reinterpret_cast<const void*>(lovr::attention_simt_kernel<false>), smem)) return rc;
     if (f16)
       lovr::attention_simt_kernel<true><<<n_img * H, lovr::kSimtAttnWarps * 32, smem, s>>>(
           static_cast<const uint16_t*>(qkv), static_cast<uint16_t*>(out), T, H, 0.125f);
@@ -383,11 +385,7 @@ int launch_attention(const void* qkv, void* out, int n_img, int T, int H, int im
 #define LOVR_ATTN4_LAUNCH(F16_, RC_)                                                                                  \
   do {                                                                                                               \
     auto kern = lovr::attention4_tcgen05_kernel<F16_, RC_>;                                                             \
-    static size_t set_for4 = 0;                                                                                      \
-    if (smem4 > set_for4) {                                                                                          \
-      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem4)));    \
-      set_for4 = smem4;                                                                                              \
-    }                                                                                                                \
+    if (int rc_ = ensure_smem(reinterpret_cast<const void*>(kern), smem4)) return rc_;                                 \
     kern<<<grid, lovr::kAttn3Threads, smem4, s>>>(tq, a);                                                            \
   } while (0)
     if (f16) LOVR_ATTN4_LAUNCH(true, lovr::kAttn4ControlRegs); else LOVR_ATTN4_LAUNCH(false, lovr::kAttn4ControlRegs);
@@ -403,11 +401,7 @@ int launch_attention(const void* qkv, void* out, int n_img, int T, int H, int im
 #define LOVR_ATTN3_LAUNCH(F16_, PIPE_)                                                                                \
   do {                                                                                                               \
     auto kern = lovr::attention3_tcgen05_kernel<F16_, PIPE_>;                                                        \
-    static size_t set_for3 = 0;                                                                                      \
-    if (smem3 > set_for3) {                                                                                          \
-      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem3)));    \
-      set_for3 = smem3;                                                                                              \
-    }                                                                                                                \
+    if (int rc_ = ensure_smem(reinterpret_cast<const void*>(kern), smem3)) return rc_;                                 \
     kern<<<n_img * H, lovr::kAttn3Threads, smem3, s>>>(tq, a);                                                       \
   } while (0)
     switch (pipe) {
@@ -427,11 +421,7 @@ int launch_attention(const void* qkv, void* out, int n_img, int T, int H, int im
 #define LOVR_ATTN2_LAUNCH(F16_, PT_, NP_)                                                                             \
   do {                                                                                                               \
     auto kern = lovr::attention2_tcgen05_kernel<F16_, PT_, NP_>;                                                     \
-    static size_t set_for2 = 0;                                                                                      \
-    if (smem2 > set_for2) {                                                                                          \
-      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem2)));    \
-      set_for2 = smem2;                                                                                              \
-    }                                                                                                                \
+    if (int rc_ = ensure_smem(reinterpret_cast<const void*>(kern), smem2)) return rc_;                                 \
     kern<<<n_img * H, threads, smem2, s>>>(tq, a);                                                                   \
   } while (0)
     if (np == 3) { if (f16) LOVR_ATTN2_LAUNCH(true, true, 3); else LOVR_ATTN2_LAUNCH(false, true, 3); }
@@ -442,14 +432,8 @@ int launch_attention(const void* qkv, void* out, int n_img, int T, int H, int im
     return 0;
   }
   const size_t smem = lovr::attn_smem_bytes(nb);
-  static size_t set_for = 0;
-  if (smem > set_for) {
-    CUDA_TRY(cudaFuncSetAttribute(lovr::attention_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(smem)));
-    CUDA_TRY(cudaFuncSetAttribute(lovr::attention_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(smem)));
-    set_for = smem;
-  }
+  if (int rc = ensure_smem(reinterpret_cast<const void*>(lovr::attention_tcgen05_kernel<true>), smem)) return rc;
+  if (int rc = ensure_smem(reinterpret_cast<const void*>(lovr::attention_tcgen05_kernel<false>), smem)) return rc;
   if (f16) lovr::attention_tcgen05_kernel<true><<<n_img * H, lovr::kAttnThreads, smem, s>>>(tq, a);
   else lovr::attention_tcgen05_kernel<false><<<n_img * H, lovr::kAttnThreads, smem, s>>>(tq, a);
   LAUNCH_CHECK("attention_tcgen05_kernel");
@@ -1047,38 +1031,44 @@ int lovr_c_score_keypoints(const void* desc1, const void* desc2, int32_t dtype, 
   if (n_pairs > 65535) return fail(LOVR_E_ARG, "c_score_keypoints: at most 65535 pairs per call");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   float* rows = static_cast<float*>(workspace);
-  const size_t smem = static_cast<size_t>(K) * D * 4;
+  // The K normalised source rows live in shared memory (K * D floats).  SPair-71k pads to 30 keypoints and the two-model
+  // concat has D = 2048: 240 KB, above the 227 KB a block may opt in to — so K is split into equal chunks that fit.
+  constexpr size_t kKpSmemBudget = 200 * 1024;
+  const int kc_max = static_cast<int>(kKpSmemBudget / (static_cast<size_t>(D) * 4));
+  if (kc_max < 1) return fail(LOVR_E_UNSUPPORTED, "c_score_keypoints: D=%d: one source row exceeds the shared-memory budget", D);
+  const int n_chunks = (K + kc_max - 1) / kc_max;
+  const int kc = (K + n_chunks - 1) / n_chunks;
   const int rpb = 64;
   dim3 grid((PP + rpb - 1) / rpb, static_cast<unsigned>(n_pairs));
-#define LOVR_KP_LAUNCH(KERN_, ...)                                                                                    \
-  do {                                                                                                               \
-    static size_t set_for = 0;                                                                                       \
-    if (smem > set_for) {                                                                                            \
-      CUDA_TRY(cudaFuncSetAttribute(KERN_, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));    \
-      set_for = smem;                                                                                                \
-    }                                                                                                                \
-    KERN_<<<grid, 256, smem, s>>>(__VA_ARGS__);                                                                      \
-  } while (0)
   const float* f1 = static_cast<const float*>(desc1);
   const float* f2 = static_cast<const float*>(desc2);
   const __nv_bfloat16* h1 = static_cast<const __nv_bfloat16*>(desc1);
   const __nv_bfloat16* h2 = static_cast<const __nv_bfloat16*>(desc2);
   const bool f32 = dtype == LOVR_DT_F32;
-  if (D == 1024) {
-    if (f32) LOVR_KP_LAUNCH((kp_sim_rows4_kernel<float, 8>), f1, f2, patch_idx, K, PP, rpb, rows);
-    else LOVR_KP_LAUNCH((kp_sim_rows4_kernel<__nv_bfloat16, 8>), h1, h2, patch_idx, K, PP, rpb, rows);
-  } else if (D == 768) {
-    if (f32) LOVR_KP_LAUNCH((kp_sim_rows4_kernel<float, 6>), f1, f2, patch_idx, K, PP, rpb, rows);
-    else LOVR_KP_LAUNCH((kp_sim_rows4_kernel<__nv_bfloat16, 6>), h1, h2, patch_idx, K, PP, rpb, rows);
-  } else if (D == 2048) {
-    if (f32) LOVR_KP_LAUNCH((kp_sim_rows4_kernel<float, 16>), f1, f2, patch_idx, K, PP, rpb, rows);
-    else LOVR_KP_LAUNCH((kp_sim_rows4_kernel<__nv_bfloat16, 16>), h1, h2, patch_idx, K, PP, rpb, rows);
-  } else {
-    if (f32) LOVR_KP_LAUNCH(kp_sim_rows_kernel<float>, f1, f2, patch_idx, K, PP, D, rpb, rows);
-    else LOVR_KP_LAUNCH(kp_sim_rows_kernel<__nv_bfloat16>, h1, h2, patch_idx, K, PP, D, rpb, rows);
-  }
+  for (int k0 = 0; k0 < K; k0 += kc) {
+    const int kn = K - k0 < kc ? K - k0 : kc;
+    const size_t smem = static_cast<size_t>(kn) * D * 4;
+#define LOVR_KP_LAUNCH(KERN_, ...)                                                        \
+  do {                                                                                   \
+    if (int rc_ = ensure_smem(reinterpret_cast<const void*>(&KERN_), smem)) return rc_;  \
+    KERN_<<<grid, 256, smem, s>>>(__VA_ARGS__);                                          \
+  } while (0)
+    if (D == 1024) {
+      if (f32) LOVR_KP_LAUNCH((kp_sim_rows4_kernel<float, 8>), f1, f2, patch_idx, K, k0, kn, PP, rpb, rows);
+      else LOVR_KP_LAUNCH((kp_sim_rows4_kernel<__nv_bfloat16, 8>), h1, h2, patch_idx, K, k0, kn, PP, rpb, rows);
+    } else if (D == 768) {
+      if (f32) LOVR_KP_LAUNCH((kp_sim_rows4_kernel<float, 6>), f1, f2, patch_idx, K, k0, kn, PP, rpb, rows);
+      else LOVR_KP_LAUNCH((kp_sim_rows4_kernel<__nv_bfloat16, 6>), h1, h2, patch_idx, K, k0, kn, PP, rpb, rows);
+    } else if (D == 2048) {
+      if (f32) LOVR_KP_LAUNCH((kp_sim_rows4_kernel<float, 16>), f1, f2, patch_idx, K, k0, kn, PP, rpb, rows);
+      else LOVR_KP_LAUNCH((kp_sim_rows4_kernel<__nv_bfloat16, 16>), h1, h2, patch_idx, K, k0, kn, PP, rpb, rows);
+    } else {
+      if (f32) LOVR_KP_LAUNCH(kp_sim_rows_kernel<float>, f1, f2, patch_idx, K, k0, kn, PP, D, rpb, rows);
+      else LOVR_KP_LAUNCH(kp_sim_rows_kernel<__nv_bfloat16>, h1, h2, patch_idx, K, k0, kn, PP, D, rpb, rows);
+    }
 #undef LOVR_KP_LAUNCH
-  LAUNCH_CHECK("kp_sim_rows_kernel");
+    LAUNCH_CHECK("kp_sim_rows_kernel");
+  }
   return launch_flow_rows(rows, PP, static_cast<size_t>(n_pairs) * K, P, window, soft, anno_size / P, kps_out, nullptr, s);
 }
 
@@ -1138,7 +1128,7 @@ CkaLayout cka_layout(int64_t R, int Dx, int Dy) {
 
 size_t lovr_cka_workspace_bytes(int64_t rows, int32_t Dx, int32_t Dy) { return cka_layout(rows, Dx, Dy).total; }
 size_t lovr_cka_gram_elems(int32_t Dx, int32_t Dy) {
-  return static_cast<size_t>(Dx) * (Dx + Dy) + static_cast<size_t>(Dy) * Dy + Dx + Dy;
+  return static_cast<size_t>(Dx) * (Dx + Dy) + static_cast<size_t>(Dy) * Dy + Dx + Dy + 1;  // last element: row count
 }
 
 int lovr_cka_accumulate(const void* X, const void* Y, int64_t rows, int32_t Dx, int32_t Dy, double* gram, void* workspace,
@@ -1180,8 +1170,10 @@ int lovr_cka_accumulate(const void* X, const void* Y, int64_t rows, int32_t Dx, 
     g.bias = nullptr; g.colscale = nullptr; g.rowscale = nullptr; g.rowmax = nullptr; g.n_valid = N; g.scale_ld = 0;
     if ((rc = launch_gemm(256, EPI_F32, ACT_NONE, false, ta, tb, tc, g, s))) return rc;
     const size_t n = static_cast<size_t>(M) * N;
-    reduce_partials_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(c_ptr, n, l.splits, n,
-                                                                                  part == 0 ? gram : gram + na);
+    // the row count travels in the same buffer (its last element), so the multi-GPU path needs ONE all-reduce
+    reduce_partials_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(
+        c_ptr, n, l.splits, n, part == 0 ? gram : gram + na, part == 0 ? gram + na + nb + Dz : nullptr,
+        static_cast<double>(rows));
     LAUNCH_CHECK("reduce_partials_kernel");
   }
   return 0;
@@ -1193,7 +1185,8 @@ int lovr_cka_finalize(const double* gram, double n_rows, int32_t Dx, int32_t Dy,
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   CUDA_TRY(cudaMemsetAsync(out3, 0, 3 * sizeof(double), s));
   const size_t na = static_cast<size_t>(Dx) * (Dx + Dy), nb = static_cast<size_t>(Dy) * Dy;
-  lovr::cka_finalize_kernel<<<296, 256, 0, s>>>(gram, gram + na, gram + na + nb, n_rows, Dx, Dy, out3);
+  // n_rows <= 0: use the count accumulated in the buffer's last element (summed over ranks by the same all-reduce)
+  lovr::cka_finalize_kernel<<<296, 256, 0, s>>>(gram, gram + na, gram + na + nb, n_rows, gram + na + nb + Dx + Dy, Dx, Dy, out3);
   LAUNCH_CHECK("cka_finalize_kernel");
   return 0;
 }

@@ -6,7 +6,7 @@ sum over ranks of small partial-sum buffers:
     extraction : contiguous image shard per rank, NO collective
     A score    : [sum_336, sum_224, n_images]                      -> one all-reduce(sum)
     C score    : [n_categories, 4] category partial sums             -> one all-reduce(sum)
-    linear CKA : fp64 uncentred Gram + column sums (~25 MB @ D=1024) -> one all-reduce(sum)
+    linear CKA : fp64 uncentred Gram + column sums + row count in ONE buffer (~25 MB @ D=1024) -> one all-reduce(sum)
 """
 import os
 
@@ -54,9 +54,8 @@ def c_score_reduce(category_sums):
     return weighted_c_score(all_reduce_sum(category_sums.clone()))
 
 
-def cka_reduce(gram, n_rows, Dx, Dy):
+def cka_reduce(gram, Dx, Dy):
+    """One all-reduce: the per-shard Gram sums, column sums AND row count live in the same fp64 buffer (cka.cka_gram)."""
     from .cka import cka_from_gram
-    n = torch.tensor([float(n_rows)], dtype=torch.float64, device=gram.device)
     all_reduce_sum(gram)
-    all_reduce_sum(n)
-    return cka_from_gram(gram, n.item(), Dx, Dy)
+    return cka_from_gram(gram, None, Dx, Dy)

@@ -8,7 +8,11 @@ and C_score/extract_feature.py:54-130 (batch-1 tower forward, `[1,C,h,w]` layout
   * `FeatureExtractor.run(...)`       chunked, double-buffered pipeline on three CUDA streams: H2D of chunk i+1 and
                                       D2H of chunk i-1 overlap the tower forward of chunk i (pinned host memory).
   * `to_c_score_layout(f, h, w)`      `[1,P,C] -> [1,C,h,w]` exactly as extract_feature.py:82 (`permute(0,2,1).view`).
+  * `extract_folder(...)`             the dataset-level driver: walk a directory, shard it over ranks, skip images whose
+                                      `.pt` exists, write per-image files in the reference's two layouts, final barrier.
 """
+import os
+
 import torch
 
 from . import towers as T
@@ -106,11 +110,12 @@ class FeatureExtractor:
                 host_out[s:e].copy_(b["out"][k][: e - s], non_blocking=True)
                 b["out_free"][k].record(self._copy_out)
         main.wait_stream(self._copy_out)
+        self._copy_out.synchronize()      # the D2H copies are asynchronous: the host may only read host_out after this
         return host_out
 
 
     @torch.no_grad()
-    def run_images(self, images, host_out=None, pixel_dtype=torch.bfloat16, pad_square=False):
+    def run_images(self, images, host_out=None, pixel_dtype=torch.bfloat16, pad_square=False, pre_cfgs=None):
         """Raw images (PIL images or HWC uint8 arrays, any sizes) -> pinned CPU features [N,P,sum(hidden)].
 
         The reference preprocesses on the CPU (DataLoader workers + HF processors, llava/feature/extract.py:176-190;
@@ -122,8 +127,10 @@ class FeatureExtractor:
         n = len(images)
         if n == 0:
             raise ValueError("no images")
-        procs = [t.image_processor for t in self.towers]
-        sizes = [p.crop_size["height"] for p in procs]
+        # pre_cfgs: one lovr_preprocess configuration per tower instead of the towers' own HF processors (the C-score
+        # walker passes the `resize + (x/255 - .5)*2` map of C_score/extract_feature.py:65-67)
+        cfgs = list(pre_cfgs) if pre_cfgs is not None else [t.image_processor._cfg(pad_square) for t in self.towers]
+        sizes = [int(c.crop_size) for c in cfgs]
         toks = {t.out_tokens(r) for t, r in zip(self.towers, sizes)}
         if len(toks) != 1:
             raise RuntimeError(f"towers disagree on token count: {sorted(toks)}")
@@ -146,8 +153,8 @@ class FeatureExtractor:
             main.wait_event(b["in_ready"][k])
             main.wait_event(b["out_free"][k])
             off = 0
-            for t, p, d in zip(self.towers, procs, b["px"][k]):
-                PP.run_packed(dev_raw, offsets, hw, p._cfg(pad_square), out=d[: e - s])
+            for t, cfg, d in zip(self.towers, cfgs, b["px"][k]):
+                PP.run_packed(dev_raw, offsets, hw, cfg, out=d[: e - s])
                 t.forward_into(d[: e - s], b["out"][k][: e - s], off)
                 off += t.hidden_size
             b["fwd_done"][k].record(main)
@@ -156,7 +163,96 @@ class FeatureExtractor:
                 host_out[s:e].copy_(b["out"][k][: e - s], non_blocking=True)
                 b["out_free"][k].record(self._copy_out)
         main.wait_stream(self._copy_out)
+        self._copy_out.synchronize()      # the D2H copies are asynchronous: the host may only read host_out after this
         return host_out
+
+
+IMAGE_EXTENSIONS = (".jpg", ".jpeg", ".png")      # C_score/extract_feature.py:113
+
+
+def list_images(input_dir):
+    """The walk of C_score/extract_feature.py:110-118 made deterministic (directories and files in sorted order, so every
+    rank sees the same list): -> [(class_name = basename of the containing directory, image stem, path)]."""
+    items = []
+    for root, dirs, files in os.walk(input_dir):
+        dirs.sort()
+        for f in sorted(files):
+            if f.endswith(IMAGE_EXTENSIONS):
+                items.append((os.path.basename(root), os.path.splitext(f)[0], os.path.join(root, f)))
+    return items
+
+
+def _load_rgb(path):
+    from PIL import Image
+    with Image.open(path) as im:
+        return im.convert("RGB")
+
+
+def extract_folder(extractor, input_dir, output_dir, layout="c_score", model_tag="dino336", img_size=None, rank=None,
+                   world=None, batch=256, loader=_load_rgb, barrier=True):
+    """Dataset-level data-parallel extraction with the reference's observable contract — files.
+
+    Replaces llava/feature/extract.py:193-231,259 (`inference()`: DistributedSampler shard per rank, per-image `.pt`,
+    skip-if-exists at :225, final `dist.barrier()` at :259) and C_score/extract_feature.py:110-130 (`process_images`: walk,
+    `<output>/<class>/<image>_<tag>.pt`), with the tower forward batched instead of batch-1.
+
+      layout "c_score": pixels = `img.resize((S,S))`, `(x/255 - .5)*2` (extract_feature.py:65-67, on the device, fp32 like
+                        the reference), file = fp32 `[1, C, h, w]` = `f.permute(0,2,1).view(1,C,h,w)` (:82-90) at
+                        `<output_dir>/<class>/<stem>_<model_tag>.pt` (what pck_train.py:33-37 reads)
+      layout "tokens":  pixels = the tower's own HF processor in bf16 (extract.py:228), file = bf16 `[P, D]`
+                        (`out_list[0].squeeze().cpu()`, :230-231) at `<output_dir>/<parent dir>/<stem>.pt` (:222-231)
+
+    Sharding: the sorted image list is cut into contiguous shards (`shard_range`), one per rank; no data-path collective.
+    Images whose output file exists are dropped BEFORE anything is loaded or launched, so a finished job re-runs with zero
+    kernel launches.  Files are written through a temporary name + rename: a killed job leaves no truncated `.pt` behind
+    (which skip-if-exists would otherwise trust forever).  Returns the counts."""
+    import torch.distributed as dist
+    from . import _lib, preprocess as PP
+    if layout not in ("c_score", "tokens"):
+        raise ValueError(f"layout must be 'c_score' or 'tokens', got {layout!r}")
+    if rank is None:
+        rank = dist.get_rank() if dist.is_initialized() else 0
+    if world is None:
+        world = dist.get_world_size() if dist.is_initialized() else 1
+    items = list_images(input_dir)
+    lo, hi = shard_range(len(items), rank, world)
+
+    def out_path(cls, stem, path):
+        if layout == "c_score":
+            return os.path.join(output_dir, cls, f"{stem}_{model_tag}.pt")
+        return os.path.join(output_dir, cls, os.path.basename(path).split(".")[0] + ".pt")      # extract.py:224
+    todo = [(c, s, p) for c, s, p in items[lo:hi] if not os.path.exists(out_path(c, s, p))]
+    stats = dict(total=len(items), shard=hi - lo, skipped=(hi - lo) - len(todo), written=0, launches=0)
+    pre_cfgs, pixel_dtype = None, torch.bfloat16
+    if layout == "c_score":
+        if len(extractor.towers) != 1:
+            raise ValueError("the C-score feature files hold one tower each (pck_train_two.py loads two files)")
+        tower = extractor.towers[0]
+        size = int(img_size or tower._default_image_size())
+        cfg = _lib.PreprocessConfig()
+        cfg.resize_mode, cfg.resize_size, cfg.crop_size = _lib.RESIZE_EXACT, size, size
+        cfg.pad_square, cfg.pixel_map = 0, _lib.PIX_CSCORE
+        for i in range(3):
+            cfg.mean[i], cfg.std[i] = 0.0, 1.0
+        pre_cfgs, pixel_dtype = [cfg], torch.float32
+    launches0 = _lib.launch_count() if todo else 0
+    for s0 in range(0, len(todo), batch):
+        part = todo[s0:s0 + batch]
+        feats = extractor.run_images([loader(p) for _, _, p in part], pixel_dtype=pixel_dtype, pre_cfgs=pre_cfgs)
+        g = int(round(feats.shape[1] ** 0.5))
+        for (cls, stem, src), f in zip(part, feats):
+            path = out_path(cls, stem, src)
+            os.makedirs(os.path.dirname(path), exist_ok=True)
+            t = to_c_score_layout(f[None], g, g).clone() if layout == "c_score" else f.clone()
+            tmp = f"{path}.tmp{os.getpid()}"
+            torch.save(t, tmp)
+            os.replace(tmp, path)
+            stats["written"] += 1
+    if todo:
+        stats["launches"] = _lib.launch_count() - launches0
+    if barrier and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.barrier()      # extract.py:259: nobody leaves before every rank's files are on disk
+    return stats
 
 
 def build_extractor(selector, select_layer=-2, select_feature="patch", chunk=128, **tower_args):

@@ -7,7 +7,8 @@ Mirrors llava/model/multimodal_projector/builder.py:34-59 `build_vision_projecto
   'identity'        -> pass-through
   'perceiver{N}x'   -> out of scope here (NotImplementedError); anything else -> ValueError like the reference.
 Every Linear(+GELU) is one launch of the tcgen05 GEMM with the bias/erf-GELU epilogue fused (lovr_gemm_bf16).
-Weights: an `nn.Sequential`-style state_dict ('0.weight', '0.bias', '2.weight', ...) or seeded synthetic ones.
+Weights: the reference modules' own state_dict — `nn.Sequential` keys ('0.weight', '0.bias', '2.weight', ...) for mlpNx_gelu,
+bare `nn.Linear` keys ('weight', 'bias') for 'linear' — or seeded synthetic ones.
 """
 import re
 
@@ -51,7 +52,10 @@ class B200MlpProjector(nn.Module):
         for i in range(len(self.dims) - 1):
             key = str(2 * i)                       # nn.Sequential indices: 0, 2, 4 (GELU modules in between)
             if state_dict is not None:
-                w, b = state_dict[f"{key}.weight"], state_dict[f"{key}.bias"]
+                if f"{key}.weight" not in state_dict and len(self.dims) == 2 and "weight" in state_dict:
+                    key = ""                       # 'linear' is a bare nn.Linear in the reference (builder.py:37-38): keys 'weight' / 'bias'
+                pre = f"{key}." if key else ""
+                w, b = state_dict[pre + "weight"], state_dict[pre + "bias"]
             else:
                 w = torch.randn(self.dims[i + 1], self.dims[i], generator=g) * (self.dims[i] ** -0.5)
                 b = torch.randn(self.dims[i + 1], generator=g) * 0.02
@@ -84,8 +88,10 @@ class B200MlpProjector(nn.Module):
 
 def build_vision_projector(config, delay_load=False, **kwargs):
     projector_type = getattr(config, "mm_projector_type", "linear")
+    od = getattr(config, "lovr_operand_dtype", "bf16")
     extra = dict(state_dict=getattr(config, "lovr_projector_state_dict", None),
-                 device=getattr(config, "lovr_device", "cuda"))
+                 device=getattr(config, "lovr_device", "cuda"),
+                 operand_dtype={"bf16": torch.bfloat16, "fp16": torch.float16, "f16": torch.float16}.get(od, od))
     if projector_type == "linear":
         return B200MlpProjector([config.mm_hidden_size, config.hidden_size], **extra)
     m = re.match(r"^mlp(\d+)x_gelu$", projector_type)

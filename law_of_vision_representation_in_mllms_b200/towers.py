@@ -26,7 +26,7 @@ import torch.nn as nn
 
 from . import _lib
 from .specs import (FAMILY_CLIP, FAMILY_DINOV2, FAMILY_SIGLIP, TOWER_SPECS, TowerSpec, layers_to_run)
-from .weights import canonical_weights, synthetic_state_dict
+from .weights import DEFAULT_POS_INTERP, canonical_weights, synthetic_state_dict
 
 DEFAULT_MAX_BATCH = int(os.environ.get("LOVR_MAX_BATCH", "128"))   # images per native call; 8.3 MB of workspace each at ViT-L/336
 
@@ -157,6 +157,8 @@ class _B200VisionTower(nn.Module):
         od = getattr(self._args, "lovr_operand_dtype", os.environ.get("LOVR_OPERAND_DTYPE", "bf16"))
         self._operand_dtype = {"bf16": torch.bfloat16, "fp16": torch.float16, "f16": torch.float16,
                                torch.bfloat16: torch.bfloat16, torch.float16: torch.float16}[od]
+        # DINOv2 position-table interpolation form: the reference's pinned transformers (4.31/4.38, default) or this image's 5.5
+        self._pos_interp = getattr(self._args, "lovr_pos_interp", os.environ.get("LOVR_DINOV2_POS_INTERP", DEFAULT_POS_INTERP))
         self._native.clear()
         self._instance(self._default_image_size())
         self.image_processor = self._make_image_processor()
@@ -170,7 +172,7 @@ class _B200VisionTower(nn.Module):
         inst = self._native.get(image_size)
         if inst is None:
             spec_r = self._spec.at_resolution(image_size)     # raises like HF for fixed-resolution towers
-            cw = canonical_weights(self._spec, self._state_dict, image_size=image_size)
+            cw = canonical_weights(self._spec, self._state_dict, image_size=image_size, pos_interp=self._pos_interp)
             inst = _NativeTower(spec_r, cw, self._device, self._max_batch, self._operand_dtype)
             self._native[image_size] = inst
         return inst

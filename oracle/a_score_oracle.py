@@ -54,3 +54,25 @@ def linear_cka(X, Y):
     Yc = Y - Y.mean(0, keepdim=True)
     hsic = (Yc.T @ Xc).pow(2).sum()
     return (hsic / ((Xc.T @ Xc).pow(2).sum().sqrt() * (Yc.T @ Yc).pow(2).sum().sqrt())).item()
+
+
+def cka_gram_buffer(X, Y):
+    """The per-shard partial-sum buffer of the multi-GPU CKA path, restated in fp64 (layout documented at
+    include/lovr_b200.h `lovr_cka_accumulate`): [X^T[X|Y] (Dx x (Dx+Dy)) | Y^T Y (Dy x Dy) | column sums (Dx+Dy) | row count].
+    Sums over ranks of these buffers are sufficient statistics of linear CKA."""
+    X = X.reshape(-1, X.shape[-1]).double()
+    Y = Y.reshape(-1, Y.shape[-1]).double()
+    Z = torch.cat([X, Y], dim=1)
+    return torch.cat([(X.T @ Z).flatten(), (Y.T @ Y).flatten(), Z.sum(0), torch.tensor([float(X.shape[0])], dtype=torch.float64)])
+
+
+def cka_from_gram_buffer(buf, Dx, Dy):
+    """Centring applied after the reduction: Gc = G - s s^T / n."""
+    Dz = Dx + Dy
+    na, nb = Dx * Dz, Dy * Dy
+    Ga, Gb = buf[:na].reshape(Dx, Dz), buf[na:na + nb].reshape(Dy, Dy)
+    s, n = buf[na + nb:na + nb + Dz], buf[na + nb + Dz]
+    Gac = Ga - torch.outer(s[:Dx], s) / n
+    Gbc = Gb - torch.outer(s[Dx:], s[Dx:]) / n
+    xx, xy, yy = Gac[:, :Dx].pow(2).sum(), Gac[:, Dx:].pow(2).sum(), Gbc.pow(2).sum()
+    return (xy / (xx.sqrt() * yy.sqrt())).item()

@@ -50,7 +50,41 @@ class _Args:
 
 
 # ----------------------------------------------------------------------------------- ViT towers
-def _reference_tower(spec, sd, select_layer, select_feature):
+def _patch_dinov2_interp_438(emb):
+    """Replace transformers 5.5's `Dinov2Embeddings.interpolate_pos_encoding` by the form of the versions the reference
+    pins (4.31.0 pyproject.toml:16 / 4.38.2 run.sh:5; modeling_dinov2.py `interpolate_pos_encoding`, restated — that source
+    is not in this image): `height + 0.1`, `F.interpolate(scale_factor=height / sqrt(num_positions))`."""
+    import math
+
+    def interpolate_pos_encoding(embeddings, height, width):
+        num_patches = embeddings.shape[1] - 1
+        num_positions = emb.position_embeddings.shape[1] - 1
+        if num_patches == num_positions and height == width:
+            return emb.position_embeddings
+        class_pos_embed = emb.position_embeddings[:, 0]
+        patch_pos_embed = emb.position_embeddings[:, 1:]
+        dim = embeddings.shape[-1]
+        h = height // emb.config.patch_size + 0.1
+        w = width // emb.config.patch_size + 0.1
+        side = int(math.sqrt(num_positions))
+        patch_pos_embed = patch_pos_embed.reshape(1, side, side, dim).permute(0, 3, 1, 2)
+        target_dtype = patch_pos_embed.dtype
+        patch_pos_embed = torch.nn.functional.interpolate(
+            patch_pos_embed.to(torch.float32), scale_factor=(float(h / math.sqrt(num_positions)), float(w / math.sqrt(num_positions))),
+            mode="bicubic", align_corners=False).to(dtype=target_dtype)
+        if int(h) != patch_pos_embed.shape[-2] or int(w) != patch_pos_embed.shape[-1]:
+            raise ValueError("Width or height does not match with the interpolated position embeddings")
+        patch_pos_embed = patch_pos_embed.permute(0, 2, 3, 1).reshape(1, -1, dim)
+        return torch.cat((class_pos_embed.unsqueeze(0), patch_pos_embed), dim=1)
+    emb.interpolate_pos_encoding = interpolate_pos_encoding
+
+
+def case_pos_interp(name):
+    """Fixtures come from transformers 5.5 (this image) unless the case name ends in `_t438` (the reference's pinned form)."""
+    return "transformers-4.38" if name.endswith("_t438") else "transformers-5.5"
+
+
+def _reference_tower(spec, sd, select_layer, select_feature, pos_interp="transformers-5.5"):
     """Build the reference wrapper for `spec`, with from_pretrained stubbed to (config, sd)."""
     import transformers as T
     enc = os.path.join(REF, "llava/model/multimodal_encoder")
@@ -78,6 +112,8 @@ def _reference_tower(spec, sd, select_layer, select_feature):
         def build(*a, **k):
             m = T.Dinov2Model(cfg)
             m.load_state_dict(sd, strict=True)
+            if pos_interp == "transformers-4.38":
+                _patch_dinov2_interp_438(m.embeddings)
             return m.eval()
         mod.AutoModel = types.SimpleNamespace(from_pretrained=build)
         mod.AutoConfig = types.SimpleNamespace(from_pretrained=lambda *a, **k: cfg)
@@ -121,8 +157,28 @@ VIT_CASES = [
     ("clip336_full_hf", "openai/clip-vit-large-patch14-336", None, 336, 1, -2, "patch"),
     ("clip224_full_hf", "openai/clip-vit-large-patch14", None, 224, 2, -2, "patch"),
     ("dinov2_336_full_hf", "facebook/dinov2-large", None, 336, 1, -2, "patch"),
+    # "_t438": DINOv2 position interpolation of the reference's pinned transformers (scale_factor + 0.1 form)
+    ("dinov2_336_l3_t438", "facebook/dinov2-large", 3, 336, 2, -2, "patch"),
+    ("dinov2_224_l3_t438", "facebook/dinov2-large", 3, 224, 2, -2, "patch"),
+    # round 2: every family at full depth on the benchmark (HF-init) weights ...
+    ("siglip224_full_hf", "google/siglip-base-patch16-224", None, 224, 2, -2, "cls_patch"),
+    ("openclip224_full_hf", "laion/CLIP-ViT-L-14-laion2B-s32B-b82K", None, 224, 1, -2, "patch"),
+    # ... "_raw": the same draw NOT pre-rounded to bf16 (weight quantisation inside the measured error) ...
+    ("clip336_full_raw", "openai/clip-vit-large-patch14-336", None, 336, 1, -2, "patch"),
+    ("dinov2_336_full_raw", "facebook/dinov2-large", None, 336, 1, -2, "patch"),
+    ("siglip224_full_raw", "google/siglip-base-patch16-224", None, 224, 2, -2, "cls_patch"),
+    # ... "_outlier": massive-activation channels (|x| > 100 in the residual), wide LayerNorm gains, sharp softmax, fp32 weights
+    ("clip336_full_outlier", "openai/clip-vit-large-patch14-336", None, 336, 1, -2, "patch"),
+    ("dinov2_336_full_outlier", "facebook/dinov2-large", None, 336, 1, -2, "patch"),
 ]
 VIT_TOKENS = 12   # token rows kept per image
+
+
+def case_style(name):
+    for suffix, style in (("_hf", "hf_init"), ("_raw", "hf_init_raw"), ("_outlier", "outlier")):
+        if name.endswith(suffix):
+            return style
+    return "stress"
 
 
 def vit_case_inputs(case):
@@ -131,7 +187,7 @@ def vit_case_inputs(case):
     if nl is not None:
         spec = S.tiny_spec(spec, nl)
     seed = 100 + sum(map(ord, name)) % 1000
-    sd = synthetic_state_dict(spec, seed=seed, style="hf_init" if name.endswith("_hf") else "stress")
+    sd = synthetic_state_dict(spec, seed=seed, style=case_style(name))
     imgs = synthetic_images(n, size, seed=seed + 1)
     return spec, sd, imgs
 
@@ -142,33 +198,44 @@ def token_rows(T):
     return sorted(set(rows + [0, T - 1]))
 
 
-def make_vit():
+def make_vit(only=None):
     for case in VIT_CASES:
         name, key, nl, size, n, sl, sf = case
+        if only and name not in only:
+            continue
         spec, sd, imgs = vit_case_inputs(case)
-        tower = _reference_tower(spec, sd, sl, sf)
+        tower = _reference_tower(spec, sd, sl, sf, case_pos_interp(name))
         with torch.no_grad():
             out = tower(imgs)                       # [N,P,D] fp32
             out_list = None
             if name == "clip336_l3":                # the list-of-3D-tensors calling convention
                 out_list = tower([im for im in imgs])
         rows = token_rows(out.shape[1])
-        ref_bf16_rel = None
+        ref_bf16_rel = ref_fp16_rel = None
         if spec.family != S.FAMILY_SIGLIP:
-            # the reference's own reduced-precision path (tower cast to bf16: llava/feature/extract.py:228)
+            # the reference's own reduced-precision paths: tower cast to bf16 (llava/feature/extract.py:228) and to
+            # fp16 (the eval path, llava/model/builder.py:143)
             with torch.no_grad():
                 tower.vision_tower.to(torch.bfloat16)
                 o16 = tower(imgs[:1].to(torch.bfloat16)).float()
+                ref_bf16_rel = ((o16 - out[:1]).norm() / out[:1].norm()).item()
+                try:
+                    tower.vision_tower.to(torch.float16)
+                    o16 = tower(imgs[:1].to(torch.float16)).float()
+                    ref_fp16_rel = ((o16 - out[:1]).norm() / out[:1].norm()).item()
+                except Exception as ex:      # an op without a CPU half kernel: recorded as absent
+                    print("  (reference fp16 path not runnable on this CPU:", str(ex)[:80], ")")
                 tower.vision_tower.to(torch.float32)
-            ref_bf16_rel = ((o16 - out[:1]).norm() / out[:1].norm()).item()
         rec = dict(case=case, shape=tuple(out.shape), rows=rows, values=out[:, rows].clone(),
                    fro=out.flatten(1).norm(dim=1), mean=out.flatten(1).mean(dim=1),
-                   abs_mean=out.abs().flatten(1).mean(dim=1), ref_bf16_rel=ref_bf16_rel)
+                   abs_mean=out.abs().flatten(1).mean(dim=1), ref_bf16_rel=ref_bf16_rel, ref_fp16_rel=ref_fp16_rel,
+                   abs_max=out.abs().max().item(), weight_style=case_style(name), pos_interp=case_pos_interp(name))
         if out_list is not None:
             rec["list_equal_batch"] = bool(all(torch.allclose(o[0], out[i], atol=1e-5) for i, o in enumerate(out_list)))
             rec["list_shapes"] = [tuple(o.shape) for o in out_list]
         torch.save(rec, os.path.join(GOLD, f"vit_{name}.pt"))
-        print("vit", name, tuple(out.shape), "fro", rec["fro"].tolist(), "ref bf16 rel", ref_bf16_rel, flush=True)
+        print("vit", name, tuple(out.shape), "fro", rec["fro"].tolist(), "ref bf16 rel", ref_bf16_rel, "ref fp16 rel",
+              ref_fp16_rel, flush=True)
 
 
 # ----------------------------------------------------------------------------------- A score
@@ -261,6 +328,39 @@ def make_flip():
     torch.save(out, os.path.join(GOLD, "c_score_flip.pt"))
 
 
+# ----------------------------------------------------------------------------------- mm_projector
+def make_projector():
+    """llava/model/multimodal_projector/builder.py:34-59 `build_vision_projector` itself builds the module (loaded by path
+    inside a stub package: its one relative import, perceiver_helpers, is only needed by the out-of-scope 'perceiver'
+    branch and is stubbed when it cannot be imported); seeded weights are loaded through the module's OWN state_dict keys,
+    so the key naming ('0.weight' / bare 'weight' for 'linear') is pinned as well.  Fixture: fp32 outputs + the key list."""
+    pkg = types.ModuleType("ref_mm_projector")
+    pkg.__path__ = [os.path.join(REF, "llava/model/multimodal_projector")]
+    sys.modules["ref_mm_projector"] = pkg
+    try:
+        sys.modules["ref_mm_projector.perceiver_helpers"] = _load(
+            os.path.join(REF, "llava/model/multimodal_projector/perceiver_helpers.py"), "ref_mm_projector.perceiver_helpers")
+    except Exception as ex:
+        print("  (perceiver_helpers not importable here, stubbed:", str(ex)[:80], ")")
+        sys.modules["ref_mm_projector.perceiver_helpers"] = types.SimpleNamespace(PerceiverResampler=None)
+    b = _load(os.path.join(REF, "llava/model/multimodal_projector/builder.py"), "ref_mm_projector.builder")
+    out = {}
+    for name in synth.PROJECTOR_CASES:
+        ptype, din, dh, linears, x = synth.projector_inputs(name)
+        cfg = types.SimpleNamespace(mm_projector_type=ptype, mm_hidden_size=din, hidden_size=dh)
+        mod = b.build_vision_projector(cfg)
+        lin = [m for m in mod.modules() if isinstance(m, torch.nn.Linear)]
+        assert len(lin) == len(linears)
+        with torch.no_grad():
+            for m, (w, bias) in zip(lin, linears):
+                m.weight.copy_(w)
+                m.bias.copy_(bias)
+            y = mod(x)
+        out[name] = dict(keys=list(mod.state_dict().keys()), out=y.clone())
+        print("projector", name, out[name]["keys"], tuple(y.shape), y.norm().item())
+    torch.save(out, os.path.join(GOLD, "projector.pt"))
+
+
 # ----------------------------------------------------------------------------------- preprocessing
 def make_preprocess():
     """Outputs are bit-exact quantities: the fixture stores their SHA-256 (+ shape and a few samples), not the tensors."""
@@ -311,8 +411,12 @@ def make_preprocess():
 
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
-    what = sys.argv[1:] or ["vit", "ascore", "cscore", "preprocess", "flip"]
+    what = sys.argv[1:] or ["vit", "ascore", "cscore", "preprocess", "flip", "projector"]
+    if any(w.startswith("vit:") for w in what):      # `vit:<case>` regenerates single ViT cases
+        what.append("vit")
     torch.set_num_threads(os.cpu_count())
+    if "projector" in what:
+        make_projector()
     if "preprocess" in what:
         make_preprocess()
     if "flip" in what:
@@ -322,4 +426,4 @@ if __name__ == "__main__":
     if "cscore" in what:
         make_cscore()
     if "vit" in what:
-        make_vit()
+        make_vit(only=[w[4:] for w in what if w.startswith("vit:")] or None)

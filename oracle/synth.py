@@ -139,3 +139,25 @@ def flip_case(cfg):
     for i in cfg["invisible"]:
         kps2[i, 2] = 0.0
     return d1, d1f, d2, kps1, kps2
+
+
+# ----------------------------------------------------------------------------------- mm_projector
+PROJECTOR_CASES = {
+    # name: (mm_projector_type, mm_hidden_size, hidden_size, tokens)
+    "mlp2x_gelu_1024": ("mlp2x_gelu", 1024, 4096, 24),
+    "mlp2x_gelu_2048": ("mlp2x_gelu", 2048, 4096, 16),
+    "linear_1024": ("linear", 1024, 4096, 24),
+    "mlp3x_gelu_768": ("mlp3x_gelu", 768, 1024, 24),
+}
+
+
+def projector_inputs(name):
+    """Seeded fp32 weights (NOT rounded to 16 bits) for every Linear of the projector, in build order, and the input."""
+    ptype, din, dh, tokens = PROJECTOR_CASES[name]
+    depth = 1 if ptype == "linear" else int(ptype[3])
+    g = torch.Generator().manual_seed(500 + sum(map(ord, name)))
+    dims = [din] + [dh] * depth
+    linears = [(torch.randn(dims[i + 1], dims[i], generator=g) * dims[i] ** -0.5, torch.randn(dims[i + 1], generator=g) * 0.1)
+               for i in range(depth)]
+    x = torch.randn(2, tokens, din, generator=g)
+    return ptype, din, dh, linears, x

@@ -22,6 +22,13 @@ def _free_port():
         return s.getsockname()[1]
 
 
+def _cka_data():
+    g = torch.Generator().manual_seed(5)
+    X = torch.randn(1001, 48, generator=g) + 0.3
+    Y = 0.5 * X[:, :32] + torch.randn(1001, 32, generator=g)
+    return X, Y
+
+
 def _worker(rank, world, port, out_dir):
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     r, w = D.init_from_env(backend="gloo")
@@ -38,7 +45,12 @@ def _worker(rank, world, port, out_dir):
     lo, hi = shard_range(7, rank, world)
     sums = CS.category_sums(pck[lo:hi], cats[lo:hi], 3)
     c = D.c_score_reduce(sums)
-    torch.save(dict(a=a, c=c), os.path.join(out_dir, f"rank{rank}.pt"))
+    # linear CKA: rows sharded, ONE all-reduce of the partial-sum buffer (Gram sums + column sums + row count)
+    X, Y = _cka_data()
+    lo, hi = shard_range(X.shape[0], rank, world)
+    buf = D.all_reduce_sum(ao.cka_gram_buffer(X[lo:hi], Y[lo:hi]))
+    cka = ao.cka_from_gram_buffer(buf, X.shape[1], Y.shape[1])
+    torch.save(dict(a=a, c=c, cka=cka, cka_rows=buf[-1].item()), os.path.join(out_dir, f"rank{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -64,6 +76,9 @@ def test_world2_gloo_scores_equal_single_process(tmp_path):
     cats = np.array([0, 1, 1, 2, 0, 2, 2])
     means = [pck[cats == k, 0].double().mean().item() for k in range(3)]
     want_c = float(np.average(means, weights=[2, 2, 3]))
+    X, Y = _cka_data()
+    want_cka = ao.linear_cka(X, Y)
     for r in res:
+        assert r["cka_rows"] == 1001 and abs(r["cka"] - want_cka) < 1e-12
         assert abs(r["a"] - want_a) < 1e-12
         assert abs(r["c"][0] - want_c) < 1e-12

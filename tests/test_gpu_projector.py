@@ -35,6 +35,27 @@ def test_projector_matches_torch_sequential(ptype, din):
     assert G.rel_err(got32.cpu(), want) < 2.5e-3
 
 
+@pytest.mark.parametrize("name", ["mlp2x_gelu_1024", "mlp2x_gelu_2048", "linear_1024", "mlp3x_gelu_768"])
+@pytest.mark.parametrize("od,tol", [("bf16", 4e-3), ("fp16", 6e-4)])
+def test_projector_matches_reference_builder_fixture(name, od, tol, golden_dir):
+    """tests/golden/projector.pt: outputs of the module the reference's own build_vision_projector
+    (llava/model/multimodal_projector/builder.py:34-59, loaded by path in oracle/make_golden.py) builds, with seeded fp32
+    weights; the weights enter here through the reference module's own state_dict keys ('linear' = bare 'weight'/'bias')."""
+    import os
+    from oracle import synth
+    rec = torch.load(os.path.join(golden_dir, "projector.pt"))[name]
+    ptype, din, dh, linears, x = synth.projector_inputs(name)
+    flat = [t for wb in linears for t in wb]
+    sd = dict(zip(rec["keys"], flat))
+    cfg = types.SimpleNamespace(mm_projector_type=ptype, mm_hidden_size=din, hidden_size=dh, lovr_projector_state_dict=sd,
+                                lovr_operand_dtype=od)
+    got = P.build_vision_projector(cfg)(x.cuda())
+    assert got.dtype == torch.float32 and tuple(got.shape) == tuple(rec["out"].shape)
+    rel = G.rel_err(got.cpu(), rec["out"])
+    print(f"projector {name} {od}: rel {rel:.2e}")
+    assert rel < tol, rel
+
+
 def test_projector_type_errors():
     with pytest.raises(ValueError, match="Unknown projector type"):
         P.build_vision_projector(types.SimpleNamespace(mm_projector_type="bogus", mm_hidden_size=1024, hidden_size=4096))

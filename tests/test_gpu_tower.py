@@ -22,7 +22,7 @@ import torch
 from law_of_vision_representation_in_mllms_b200 import _lib, specs as S, towers
 from law_of_vision_representation_in_mllms_b200.weights import canonical_weights, synthetic_images
 from oracle import vit_oracle
-from oracle.make_golden import VIT_CASES, vit_case_inputs
+from oracle.make_golden import VIT_CASES, case_pos_interp, case_style, vit_case_inputs
 import gpu_util as G
 
 pytestmark = pytest.mark.gpu
@@ -32,10 +32,14 @@ _CLS = {S.FAMILY_CLIP: towers.CLIPVisionTower, S.FAMILY_DINOV2: towers.DinoV2Vis
         S.FAMILY_SIGLIP: towers.SigLipVisionTower}
 
 
+OUTLIER_CHANNELS = (7, 300)      # weights._outlier_state_dict
+
+
 def tolerance_for(name, rec):
-    if name.endswith("_hf"):
-        return 0.4 * rec["ref_bf16_rel"]      # bf16 operands: see module docstring; fp16 operands meet REL_TOL below
+    """bf16 operands (see module docstring): a fraction of the reference's OWN bf16-path deviation from its fp32 path."""
     ref = rec.get("ref_bf16_rel")
+    if case_style(name) in ("hf_init", "hf_init_raw"):
+        return 0.4 * ref if ref is not None else 6e-3       # SigLIP: the reference's wrapper does not run on the CPU
     return 0.75 * ref if ref is not None else 1.2e-2
 
 
@@ -44,7 +48,7 @@ def _build(case, attn_impl=_lib.ATTN_AUTO, operand_dtype="bf16"):
     spec, sd, imgs = vit_case_inputs(case)
     args = types.SimpleNamespace(mm_vision_select_layer=sl, mm_vision_select_feature=sf, lovr_spec=spec,
                                  lovr_state_dict=sd, lovr_image_size=size, lovr_max_batch=4,
-                                 lovr_operand_dtype=operand_dtype)
+                                 lovr_operand_dtype=operand_dtype, lovr_pos_interp=case_pos_interp(name))
     tower = _CLS[spec.family](key, args)
     tower._attn_impl = attn_impl
     return tower, spec, sd, imgs
@@ -65,21 +69,43 @@ def test_tower_matches_reference_fixture(case, golden_dir):
     assert torch.allclose(out.float().flatten(1).norm(dim=1).cpu(), rec["fro"], rtol=2e-3)
 
 
-HF_CASES = [c for c in VIT_CASES if c[0].endswith("_hf")]
+FULL_CASES = [c for c in VIT_CASES if c[2] is None]
 
 
-@pytest.mark.parametrize("case", HF_CASES, ids=[c[0] for c in HF_CASES])
+@pytest.mark.parametrize("case", FULL_CASES, ids=[c[0] for c in FULL_CASES])
 def test_tower_fp16_operands_meet_north_star_tolerance(case, golden_dir):
-    """fp16 tensor-core operands (same kernels, same throughput; the dtype the reference's eval path casts towers to,
-    llava/model/builder.py:143) bring the full-depth towers within the north_star 1e-3 of the fp32 reference."""
+    """fp16 tensor-core operands — the mode bench.py's headline runs in, and the dtype the reference's eval path casts towers
+    to (llava/model/builder.py:143; SigLIP hard-codes it, siglip_encoder.py:59-60).  Every family at full depth:
+      * benchmark weights (`_hf`) and the same draw NOT pre-rounded to 16 bits (`_raw`: weight quantisation is inside the
+        measured error): within the north_star 1e-3 of the reference's fp32 path;
+      * stress / outlier weights (sharp softmax, |x| > 100 in the residual stream): finite, reported, and several times
+        closer to the fp32 path than the reference's OWN fp16 path (`ref_fp16_rel` in the fixture) — the CPU emulation of
+        fp16 operand rounding (oracle/vit_oracle.py, scripts/predict_tower_error.py) predicts 0.8e-3 ... 3.7e-3 there: a property of 2^-12 operand
+        rounding under those weights, not of this implementation."""
     name = case[0]
     rec = torch.load(os.path.join(golden_dir, f"vit_{name}.pt"))
     tower, spec, sd, imgs = _build(case, operand_dtype="fp16")
     assert tower.dtype == torch.float16
     out = tower(imgs.cuda())
-    rel = G.rel_err(out[:, rec["rows"]].cpu(), rec["values"])
-    print(f"{name} fp16 operands: rel {rel:.3e} (reference bf16 path {rec['ref_bf16_rel']:.3e})")
-    assert rel < REL_TOL, rel
+    assert torch.isfinite(out).all()
+    got = out[:, rec["rows"]].cpu()
+    rel = G.rel_err(got, rec["values"])
+    style = case_style(name)
+    extra = ""
+    if style == "outlier":
+        keep = [c for c in range(got.shape[-1]) if c not in OUTLIER_CHANNELS]
+        rel_rest = G.rel_err(got[..., keep], rec["values"][..., keep])
+        extra = f", excluding the outlier channels {rel_rest:.3e}, |x|max {rec['abs_max']:.0f}"
+        assert rec["abs_max"] > 100
+    print(f"{name} fp16 operands: rel {rel:.3e}{extra} (reference bf16 path {rec.get('ref_bf16_rel')}, "
+          f"reference fp16 path {rec.get('ref_fp16_rel')})")
+    if style in ("hf_init", "hf_init_raw"):
+        assert rel < REL_TOL, rel
+    else:
+        ref16 = rec.get("ref_fp16_rel")
+        assert rel < (0.5 * ref16 if ref16 is not None and style != "outlier" else 6e-3), (rel, ref16)
+        if style == "outlier":
+            assert rel_rest < 6e-3          # predicted 3.7e-3 (CLIP) by scripts/predict_tower_error.py; reference fp16 path 2.8e-2
 
 
 @pytest.mark.parametrize("cname", ["clip336_l3", "dinov2_336_l3", "siglip224_l3"])
@@ -87,7 +113,7 @@ def test_tower_matches_oracle_full_tensor_and_simt_attention(cname):
     case = next(c for c in VIT_CASES if c[0] == cname)
     name, key, nl, size, n, sl, sf = case
     tower, spec, sd, imgs = _build(case)
-    cw = canonical_weights(spec, sd, image_size=size)
+    cw = canonical_weights(spec, sd, image_size=size, pos_interp=case_pos_interp(name))
     want = vit_oracle.tower_forward(cw, spec.at_resolution(size), imgs, sl, tower.select_feature)
     out = tower(imgs.cuda()).cpu()
     e1 = G.rel_err(out, want)
