@@ -46,6 +46,11 @@ uint64_t lovr_launch_count(void);
  * (2*M*N*K per launch) and the launch count since the last read, and resets the accumulator. */
 void lovr_prof_enable(int32_t on);
 int lovr_prof_read(double* gemm_ms, double* gemm_flops, uint64_t* gemm_launches);
+/* The same accumulator per kernel class: ms / work / launches are arrays of LOVR_PROF_KINDS entries.  `work` is the
+ * algorithmic FLOP count for the tensor-bound classes (GEMM: 2*M*N*K; attention: 4*T*T*64 per (image, head)) and the
+ * algorithmic byte count for the HBM-bound ones (LayerNorm: 6 B per element).  Reading resets the accumulator. */
+enum { LOVR_PROF_GEMM = 0, LOVR_PROF_ATTENTION = 1, LOVR_PROF_LAYERNORM = 2, LOVR_PROF_OTHER = 3, LOVR_PROF_KINDS = 4 };
+int lovr_prof_read_kinds(double* ms, double* work, uint64_t* launches);
 
 /* ---------------------------------------------------------------------------------------------------
  * Vision tower (replaces the arithmetic behind CLIPVisionTower.forward / DinoV2VisionTower.forward /

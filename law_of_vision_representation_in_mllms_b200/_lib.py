@@ -21,7 +21,7 @@ PIX_HF_RESCALE_NORMALIZE, PIX_CSCORE = 0, 1
 
 # every symbol include/lovr_b200.h declares (tests/test_abi.py checks the library exports all of them)
 EXPORTS = [
-    "lovr_abi_version", "lovr_last_error", "lovr_launch_count", "lovr_prof_enable", "lovr_prof_read",
+    "lovr_abi_version", "lovr_last_error", "lovr_launch_count", "lovr_prof_enable", "lovr_prof_read", "lovr_prof_read_kinds",
     "lovr_tower_workspace_bytes", "lovr_tower_create", "lovr_tower_destroy", "lovr_tower_forward",
     "lovr_gemm_bf16", "lovr_layernorm_bf16", "lovr_attention", "lovr_im2col",
     "lovr_a_score_workspace_bytes", "lovr_a_score_maxcos",
@@ -79,6 +79,8 @@ def lib():
     L.lovr_prof_enable.argtypes = [i32]
     L.lovr_prof_read.restype = C.c_int
     L.lovr_prof_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+    L.lovr_prof_read_kinds.restype = C.c_int
+    L.lovr_prof_read_kinds.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     L.lovr_tower_workspace_bytes.restype = sz
     L.lovr_tower_workspace_bytes.argtypes = [C.POINTER(TowerConfig), i32]
     L.lovr_tower_create.restype = C.c_int
@@ -149,6 +151,17 @@ def prof_read():
     ms, fl, n = C.c_double(), C.c_double(), C.c_uint64()
     check(lib().lovr_prof_read(C.byref(ms), C.byref(fl), C.byref(n)), "lovr_prof_read")
     return ms.value, fl.value, int(n.value)
+
+
+PROF_KINDS = ("gemm", "attention", "layernorm", "other")
+
+
+def prof_read_kinds():
+    """-> {kind: (ms, work, launches)} accumulated since the last read; work = FLOPs (gemm, attention) or bytes."""
+    n = len(PROF_KINDS)
+    ms, work, cnt = (C.c_double * n)(), (C.c_double * n)(), (C.c_uint64 * n)()
+    check(lib().lovr_prof_read_kinds(ms, work, cnt), "lovr_prof_read_kinds")
+    return {k: (ms[i], work[i], int(cnt[i])) for i, k in enumerate(PROF_KINDS)}
 
 
 def torch_dtype_code(dtype):

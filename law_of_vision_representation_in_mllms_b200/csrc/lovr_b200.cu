@@ -153,7 +153,8 @@ int make_tmap(CUtensorMap* m, const void* ptr, int elem_bytes, uint64_t dim0, ui
 // per-launch duration is measured inside the timed region itself (two event records per launch).
 struct ProfRec {
   cudaEvent_t a, b;
-  double flops;
+  double work;   // FLOPs (tensor-bound kinds) or bytes (HBM-bound kinds) of this launch
+  int kind;      // LOVR_PROF_*
 };
 struct Prof {
   bool on = false;
@@ -165,7 +166,7 @@ Prof& prof() {
   static Prof p;
   return p;
 }
-bool prof_begin(cudaStream_t s, double flops, size_t* idx) {
+bool prof_begin(cudaStream_t s, double work, size_t* idx, int kind = LOVR_PROF_GEMM) {
   Prof& p = prof();
   if (!p.on) return false;
   std::lock_guard<std::mutex> g(p.mu);
@@ -177,7 +178,8 @@ bool prof_begin(cudaStream_t s, double flops, size_t* idx) {
   } else {
     if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return false;
   }
-  r.flops = flops;
+  r.work = work;
+  r.kind = kind;
   cudaEventRecord(r.a, s);
   p.recs.push_back(r);
   *idx = p.recs.size() - 1;
@@ -188,6 +190,15 @@ void prof_end(cudaStream_t s, size_t idx) {
   std::lock_guard<std::mutex> g(p.mu);
   cudaEventRecord(p.recs[idx].b, s);
 }
+
+// scope guard: times everything enqueued on `s` between construction and destruction as one record of `kind`
+struct ProfScope {
+  cudaStream_t s;
+  size_t idx = 0;
+  bool on;
+  ProfScope(cudaStream_t stream, int kind, double work) : s(stream) { on = prof_begin(s, work, &idx, kind); }
+  ~ProfScope() { if (on) prof_end(s, idx); }
+};
 
 // ------------------------------------------------------------------------------------ GEMM launch
 template <int BN, int EPI, int ACT, bool F16>
@@ -319,6 +330,7 @@ int launch_layernorm(const float* x, const float* g, const float* b, float eps, 
   const int wpb = 8;
   const unsigned grid = static_cast<unsigned>((rows + wpb - 1) / wpb);
   auto y16 = static_cast<uint16_t*>(y);
+  ProfScope prof_scope(s, LOVR_PROF_LAYERNORM, 6.0 * static_cast<double>(rows) * D);  // 4 B read + 2 B written per element
   int rc = dispatch_width(
       D,
       [&] {
@@ -339,6 +351,7 @@ int launch_layernorm(const float* x, const float* g, const float* b, float eps, 
 int launch_attention(const void* qkv, void* out, int n_img, int T, int H, int impl, bool f16, cudaStream_t s) {
   if (n_img <= 0) return 0;
   const int D = H * 64;
+  ProfScope prof_scope(s, LOVR_PROF_ATTENTION, 4.0 * T * static_cast<double>(T) * 64.0 * n_img * H);  // QK^T + PV
   if (impl == LOVR_ATTN_SIMT_CHECK) {
     const size_t smem = lovr::attn_simt_smem_bytes(T);
     if (int rc = ensure_smem(reinterpret_cast<const void*>(lovr::attention_simt_kernel<true>), smem)) return rc;
@@ -519,24 +532,36 @@ void lovr_prof_enable(int32_t on) {
   p.on = on != 0;
 }
 
-int lovr_prof_read(double* gemm_ms, double* gemm_flops, uint64_t* gemm_launches) {
+int lovr_prof_read_kinds(double* ms, double* work, uint64_t* launches) {
   Prof& p = prof();
   std::lock_guard<std::mutex> g(p.mu);
-  double ms = 0, fl = 0;
+  for (int k = 0; k < LOVR_PROF_KINDS; ++k) {
+    if (ms) ms[k] = 0;
+    if (work) work[k] = 0;
+    if (launches) launches[k] = 0;
+  }
   for (ProfRec& r : p.recs) {
     cudaError_t e = cudaEventSynchronize(r.b);
     if (e != cudaSuccess) return fail(LOVR_E_CUDA, "prof_read: %s", cudaGetErrorString(e));
     float t = 0;
     e = cudaEventElapsedTime(&t, r.a, r.b);
     if (e != cudaSuccess) return fail(LOVR_E_CUDA, "prof_read: %s", cudaGetErrorString(e));
-    ms += t;
-    fl += r.flops;
+    if (ms) ms[r.kind] += t;
+    if (work) work[r.kind] += r.work;
+    if (launches) launches[r.kind] += 1;
     p.pool.emplace_back(r.a, r.b);
   }
-  if (gemm_ms) *gemm_ms = ms;
-  if (gemm_flops) *gemm_flops = fl;
-  if (gemm_launches) *gemm_launches = p.recs.size();
   p.recs.clear();
+  return 0;
+}
+
+int lovr_prof_read(double* gemm_ms, double* gemm_flops, uint64_t* gemm_launches) {
+  double ms[LOVR_PROF_KINDS], work[LOVR_PROF_KINDS];
+  uint64_t n[LOVR_PROF_KINDS];
+  if (int rc = lovr_prof_read_kinds(ms, work, n)) return rc;
+  if (gemm_ms) *gemm_ms = ms[LOVR_PROF_GEMM];
+  if (gemm_flops) *gemm_flops = work[LOVR_PROF_GEMM];
+  if (gemm_launches) *gemm_launches = n[LOVR_PROF_GEMM];
   return 0;
 }
 

@@ -163,3 +163,22 @@ def test_two_model_concat_matches_pck_train_two(dtype):
     if dtype == torch.float32:                                    # and the reference's own normalize_feats of both models
         want2 = co.normalize_two(a[:1], b[:1])
         assert (co.normalize_feats(d1[:1].cpu()) - want2).abs().max() < 1e-6
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_keypoints_spair_padding_with_two_model_width(dtype):
+    """SPair-71k pads to 30 keypoints (utils_geoware.py `torch.zeros(30, C)`) and the clip.dinov2 two-model concat is 2048
+    wide (pck_train_two.py): 30 x 2048 fp32 source rows are 240 KB, above the 227 KB a block can opt in to — the launcher
+    splits K.  P = 60 like configs[4]."""
+    g = torch.Generator().manual_seed(21)
+    P, K, D = 60, 30, 2048
+    d1 = torch.randn(1, P * P, D, generator=g).to(dtype)
+    d2 = (0.5 * torch.roll(d1.float(), 7, dims=1) + 0.5 * torch.randn(1, P * P, D, generator=g)).to(dtype)
+    kps = torch.rand(K, 3, generator=g) * 839.0
+    idx = CS.kpts_to_patch_idx(kps, P)
+    for soft in (True, False):
+        got = CS.keypoint_transformation(d1.cuda(), d2.cuda(), idx, soft=soft, window=5).cpu()
+        want = co.keypoint_transformation(co.normalize_feats(d1.float()), co.normalize_feats(d2.float()), idx, P,
+                                          soft=soft, window=5)
+        assert tuple(got.shape[-2:]) == (K, 2)
+        assert (got.reshape(K, 2) - want).abs().max() < PIX_TOL, soft
