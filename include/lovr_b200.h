@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define LOVR_ABI_VERSION 1
+#define LOVR_ABI_VERSION 2
 
 enum { LOVR_OK = 0, LOVR_E_ARG = -1, LOVR_E_CUDA = -2, LOVR_E_UNSUPPORTED = -3, LOVR_E_NOMEM = -4 };
 enum { LOVR_DT_F32 = 0, LOVR_DT_BF16 = 1, LOVR_DT_F16 = 2 };

@@ -18,7 +18,7 @@ def test_header_symbols_are_exported():
     L = _lib.lib()
     for name in declared:
         assert hasattr(L, name), name
-    assert L.lovr_abi_version() == 1
+    assert L.lovr_abi_version() == 2
 
 
 def test_workspace_queries_need_no_gpu():
@@ -93,4 +93,4 @@ int main(void) {
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
     ver, need, bad, msg = out.stdout.split(maxsplit=3)
-    assert int(ver) == 1 and int(need) > 2 * 3 * 336 * 336 and int(bad) == 0 and "crop_size" in msg
+    assert int(ver) == 2 and int(need) > 2 * 3 * 336 * 336 and int(bad) == 0 and "crop_size" in msg
