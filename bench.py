@@ -36,7 +36,7 @@ METRIC = "images/sec ViT-L/14-336 extract"
 WORKLOAD = "CLIP ViT-L/14-336, 10k synthetic 336px images, 1xB200 feature extract (configs[1])"
 C3_PAIRS, C3_BLOCK = 10000, 250          # configs[2]; data generated in blocks seeded by the GLOBAL block index
 C4_IMAGES_PER_RANK = 6250                # configs[3]: 50k dual-tower images over 8 GPUs
-C5_PAIRS, C5_CHUNK, C5_P, C5_K, C5_CATS = 12234, 64, 60, 12, 18     # configs[4]: SPair-71k test size, P=60
+C5_PAIRS, C5_CHUNK, C5_P, C5_K, C5_CATS = 12234, 256, 60, 12, 18     # configs[4]: SPair-71k test size, P=60
 
 
 def bench_config(world, batch, chunk):
@@ -661,7 +661,7 @@ def multi_gpu_parity(dev, rank, world):
 
 def c_score_job(dev, rank, world, peaks, device_ms, max_over_ranks):
     """configs[4] at job size: 12 234 SPair-71k-shaped pairs (P = 60, D = 1024, bf16 descriptors, 12 keypoints, 18 pseudo-
-    categories) in chunks of 64 seeded by the GLOBAL chunk index; chunks sharded contiguously over ranks; per chunk the
+    categories) in chunks of 256 seeded by the GLOBAL chunk index; chunks sharded contiguously over ranks; per chunk the
     keypoint path (what pck_train.py consumes: similarity rows at the keypoints -> windowed soft-argmax -> PCK -> category
     sums) and the dense P^2 x P^2 flow (the whole matrix the reference materialises) are timed on the device; descriptor
     generation stands in for loading feature files and is not timed.  One all-reduce of the [18, 4] category sums."""

@@ -109,10 +109,11 @@ def keypoint_transformation(desc1, desc2, patch_idx, soft=True, window=5, anno_s
     patch_idx, P) for a batch of pairs: desc [B,P*P,D], patch_idx [B,K] int -> [B,K,2] (x,y) pixels."""
     d1, d2, P = _prep(desc1, desc2, 32)
     B, PP, D = d1.shape
-    idx = torch.as_tensor(np.asarray(patch_idx), dtype=torch.int32).reshape(B, -1).to(d1.device).contiguous()
-    K = idx.shape[1]
-    if idx.numel() and (int(idx.min()) < 0 or int(idx.max()) >= PP):
+    idx_host = np.asarray(patch_idx.detach().cpu() if isinstance(patch_idx, torch.Tensor) else patch_idx).reshape(B, -1)
+    if idx_host.size and (int(idx_host.min()) < 0 or int(idx_host.max()) >= PP):      # on the host: no device round trip
         raise IndexError(f"index out of bounds for dimension 0 with size {PP}")
+    idx = torch.as_tensor(idx_host.astype(np.int32)).to(d1.device).contiguous()
+    K = idx.shape[1]
     L = _lib.lib()
     dt = _lib.torch_dtype_code(d1.dtype)
     out = torch.empty(B, K, 2, dtype=torch.float32, device=d1.device)

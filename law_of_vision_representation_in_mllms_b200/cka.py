@@ -12,7 +12,7 @@ import torch
 
 from . import _lib
 
-_SLAB_ROWS = 1 << 18        # rows per native call: bounds the split-K partial buffers (128 splits x 12.6 MB at D=1024)
+_SLAB_ROWS = 1 << 30        # rows per native call (the native limit is 2^31 - 2048 rows)
 
 
 def _as_rows(t):

@@ -20,10 +20,12 @@
 #include "attention3.cuh"
 #include "attention4.cuh"
 #include "attention_simt.cuh"
+#include "ascore.cuh"
 #include "cka.cuh"
 #include "cscore.cuh"
 #include "gemm.cuh"
 #include "gemm2.cuh"
+#include "gram.cuh"
 #include "preprocess.cuh"
 #include "rowwise.cuh"
 #include "scores.cuh"
@@ -845,6 +847,39 @@ int lovr_a_score_maxcos(const void* other, const void* ref, int32_t dtype, int64
   const void* a_ptr = other;
   const void* b_ptr = ref;
   int K = D;
+  const int bn = pick_bn(y);
+  // bf16 features: the `other` norms come out of the shared-memory tiles of the GEMM itself (ascore.cuh), so `other` is read
+  // from HBM once; only `ref` gets a norm pre-pass.  Needs more k-blocks than pipeline stages (its barrier-phase argument).
+  static const int fuse_env = [] { const char* e = getenv("LOVR_A_SCORE_FUSED"); return e ? atoi(e) : 1; }();
+  if (dtype == LOVR_DT_BF16 && fuse_env && D / kBK > kAsStages) {
+    rownorm_inv_bf16_kernel<<<static_cast<unsigned>((rows_r + wpb - 1) / wpb), wpb * 32, 0, s>>>(
+        static_cast<const __nv_bfloat16*>(ref), inv_r, rows_r, D);
+    LAUNCH_CHECK("rownorm_inv_bf16_kernel");
+    size_t smem = 0;
+    const void* kern = nullptr;
+    if (bn == 128) { smem = AScoreSmem<128>::kTotal; kern = reinterpret_cast<const void*>(ascore_tcgen05_kernel<128>); }
+    else if (bn == 192) { smem = AScoreSmem<192>::kTotal; kern = reinterpret_cast<const void*>(ascore_tcgen05_kernel<192>); }
+    else { smem = AScoreSmem<256>::kTotal; kern = reinterpret_cast<const void*>(ascore_tcgen05_kernel<256>); }
+    CUtensorMap ta, tb;
+    int rc;
+    if ((rc = make_tmap(&ta, other, 2, D, x, n_pairs, D, static_cast<uint64_t>(D) * x, 64, kBM))) return rc;
+    if ((rc = make_tmap(&tb, ref, 2, D, y, n_pairs, D, static_cast<uint64_t>(D) * y, 64, bn))) return rc;
+    if ((rc = ensure_smem(kern, smem))) return rc;
+    AScoreArgs a{};
+    a.x = x; a.y = y; a.K = D; a.n_pairs = static_cast<int>(n_pairs); a.inv_ref = inv_r; a.rowmax = rowmax;
+    const long long units = static_cast<long long>(n_pairs) * ((x + kBM - 1) / kBM);
+    const int grid = units < device_info().sms ? static_cast<int>(units) : device_info().sms;
+    {
+      ProfScope prof_scope(s, LOVR_PROF_OTHER, 2.0 * x * static_cast<double>(y) * D * n_pairs);
+      if (bn == 128) ascore_tcgen05_kernel<128><<<grid, kAsThreads, smem, s>>>(ta, tb, a);
+      else if (bn == 192) ascore_tcgen05_kernel<192><<<grid, kAsThreads, smem, s>>>(ta, tb, a);
+      else ascore_tcgen05_kernel<256><<<grid, kAsThreads, smem, s>>>(ta, tb, a);
+    }
+    LAUNCH_CHECK("ascore_tcgen05_kernel");
+    pair_mean_kernel<<<static_cast<unsigned>(n_pairs), 256, 0, s>>>(rowmax, pair_score, x);
+    LAUNCH_CHECK("pair_mean_kernel");
+    return 0;
+  }
   if (dtype == LOVR_DT_BF16) {
     rownorm_inv_bf16_kernel<<<static_cast<unsigned>((rows_o + wpb - 1) / wpb), wpb * 32, 0, s>>>(
         static_cast<const __nv_bfloat16*>(other), inv_o, rows_o, D);
@@ -865,7 +900,6 @@ int lovr_a_score_maxcos(const void* other, const void* ref, int32_t dtype, int64
     b_ptr = sr;
     K = 3 * D;
   }
-  const int bn = pick_bn(y);
   CUtensorMap ta, tb;
   int rc;
   if ((rc = make_tmap(&ta, a_ptr, 2, K, x, n_pairs, K, static_cast<uint64_t>(K) * x, 64, kBM))) return rc;
@@ -1129,24 +1163,20 @@ int lovr_pck(const float* pred, const float* gt, const uint8_t* visible, const f
 
 // ====================================================================================== linear CKA
 namespace {
-// Rows per split = length of one TMEM accumulation run.  The tensor core's fp32 accumulation truncates, so the
-// error of a Gram entry grows ~3e-8 x run length (measured: 1e-4 relative on CKA at 16384); 2048 keeps CKA within
-// 1e-5 of the fp64 oracle.  Partials of all splits are summed in fp64.
-constexpr int kCkaChunk = 2048;
+// One wave of persistent CTAs: unit = (row range, upper-triangle tile of the [X|Y] Gram), see gram.cuh.  The layout depends
+// only on the sizes (148 SMs assumed for the range count; any grid size runs it correctly).
 struct CkaLayout {
-  size_t zt, pa, pb, total, rpad;
-  int splits;
+  size_t total;
+  int n_tiles, n_ranges, total_chunks;
 };
 CkaLayout cka_layout(int64_t R, int Dx, int Dy) {
   CkaLayout l{};
-  l.rpad = (static_cast<size_t>(R) + kCkaChunk - 1) / kCkaChunk * kCkaChunk;
-  l.splits = static_cast<int>(l.rpad / kCkaChunk);
-  const size_t Dz = static_cast<size_t>(Dx) + Dy;
-  size_t off = 0;
-  l.zt = off; off += align_up(Dz * l.rpad * 2, 1024);
-  l.pa = off; off += align_up(static_cast<size_t>(l.splits) * Dx * Dz * 4, 1024);
-  l.pb = off; off += align_up(static_cast<size_t>(l.splits) * Dy * Dy * 4, 1024);
-  l.total = off;
+  l.n_tiles = lovr::gram_tile_count(Dx + Dy);
+  l.total_chunks = static_cast<int>((R + lovr::kGramChunk - 1) / lovr::kGramChunk);
+  l.n_ranges = 148 / l.n_tiles;
+  if (l.n_ranges < 1) l.n_ranges = 1;
+  if (l.n_ranges > l.total_chunks) l.n_ranges = l.total_chunks > 0 ? l.total_chunks : 1;
+  l.total = align_up(static_cast<size_t>(l.n_tiles) * l.n_ranges * lovr::kGramTileElems * 4, 1024);
   return l;
 }
 }  // namespace
@@ -1163,44 +1193,35 @@ int lovr_cka_accumulate(const void* X, const void* Y, int64_t rows, int32_t Dx, 
   if (!X || !Y || !gram || !workspace) return fail(LOVR_E_ARG, "cka: null pointer");
   if (rows <= 0) return 0;
   if (Dx % 256 || Dy % 256) return fail(LOVR_E_ARG, "cka: feature widths must be multiples of 256 (got %d, %d)", Dx, Dy);
+  if (rows > 0x7fffffff - kGramChunk) return fail(LOVR_E_ARG, "cka: at most 2^31 rows per call");
   const CkaLayout l = cka_layout(rows, Dx, Dy);
   if (workspace_bytes < l.total) return fail(LOVR_E_NOMEM, "cka workspace %zu < %zu", workspace_bytes, l.total);
   if (reinterpret_cast<uintptr_t>(workspace) & 1023) return fail(LOVR_E_ARG, "workspace must be 1024-byte aligned");
-  if (l.rpad / kCkaRowsPerBlock > 65535) return fail(LOVR_E_ARG, "cka: at most %d rows per call", 65535 * kCkaRowsPerBlock);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  auto base = static_cast<uint8_t*>(workspace);
-  auto zt = reinterpret_cast<uint16_t*>(base + l.zt);
-  float* pa = reinterpret_cast<float*>(base + l.pa);
-  float* pb = reinterpret_cast<float*>(base + l.pb);
   const int Dz = Dx + Dy;
   const size_t na = static_cast<size_t>(Dx) * Dz, nb = static_cast<size_t>(Dy) * Dy;
-  double* colsum = gram + na + nb;
-  transpose_colsum_kernel<<<dim3(Dx / 64, static_cast<unsigned>(l.rpad / kCkaRowsPerBlock)), 256, 0, s>>>(
-      static_cast<const uint16_t*>(X), rows, Dx, zt, l.rpad, 0, colsum);
-  LAUNCH_CHECK("transpose_colsum_kernel");
-  transpose_colsum_kernel<<<dim3(Dy / 64, static_cast<unsigned>(l.rpad / kCkaRowsPerBlock)), 256, 0, s>>>(
-      static_cast<const uint16_t*>(Y), rows, Dy, zt, l.rpad, Dx, colsum);
-  LAUNCH_CHECK("transpose_colsum_kernel");
+  CUtensorMap tx, ty;
   int rc;
-  for (int part = 0; part < 2; ++part) {
-    const int M = part == 0 ? Dx : Dy, N = part == 0 ? Dz : Dy;
-    const uint16_t* a_ptr = part == 0 ? zt : zt + static_cast<size_t>(Dx) * l.rpad;
-    float* c_ptr = part == 0 ? pa : pb;
-    CUtensorMap ta, tb, tc;
-    if ((rc = make_tmap(&ta, a_ptr, 2, kCkaChunk, M, l.splits, l.rpad, kCkaChunk, 64, kBM))) return rc;
-    if ((rc = make_tmap(&tb, a_ptr, 2, kCkaChunk, N, l.splits, l.rpad, kCkaChunk, 64, 256))) return rc;
-    if ((rc = make_tmap(&tc, c_ptr, 4, N, M, l.splits, N, static_cast<uint64_t>(M) * N, 32, 32))) return rc;
-    GemmArgs g{};
-    g.M = M; g.N = N; g.K = kCkaChunk; g.batch = l.splits; g.n_inner = 1;
-    g.bias = nullptr; g.colscale = nullptr; g.rowscale = nullptr; g.rowmax = nullptr; g.n_valid = N; g.scale_ld = 0;
-    if ((rc = launch_gemm(256, EPI_F32, ACT_NONE, false, ta, tb, tc, g, s))) return rc;
-    const size_t n = static_cast<size_t>(M) * N;
-    // the row count travels in the same buffer (its last element), so the multi-GPU path needs ONE all-reduce
-    reduce_partials_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(
-        c_ptr, n, l.splits, n, part == 0 ? gram : gram + na, part == 0 ? gram + na + nb + Dz : nullptr,
-        static_cast<double>(rows));
-    LAUNCH_CHECK("reduce_partials_kernel");
+  if ((rc = make_tmap(&tx, X, 2, Dx, rows, 1, Dx, static_cast<uint64_t>(Dx) * rows, 64, 64))) return rc;
+  if ((rc = make_tmap(&ty, Y, 2, Dy, rows, 1, Dy, static_cast<uint64_t>(Dy) * rows, 64, 64))) return rc;
+  GramArgs g{};
+  g.R = rows; g.Dx = Dx; g.Dy = Dy; g.n_tiles = l.n_tiles; g.n_ranges = l.n_ranges; g.total_chunks = l.total_chunks;
+  g.partial = static_cast<float*>(workspace);
+  g.colsum = gram + na + nb;
+  if ((rc = ensure_smem(reinterpret_cast<const void*>(gram_tcgen05_kernel), kGramSmem))) return rc;
+  const int units = l.n_tiles * l.n_ranges;
+  const int grid = units < device_info().sms ? units : device_info().sms;
+  {
+    // executed FLOPs: only the upper-triangle tiles (the algorithmic count of SURVEY.md §8d is 2 R (Dx Dz + Dy^2))
+    ProfScope prof_scope(s, LOVR_PROF_OTHER, 2.0 * static_cast<double>(rows) * l.n_tiles * kGramTileElems);
+    gram_tcgen05_kernel<<<grid, kGramThreads, kGramSmem, s>>>(tx, ty, g);
   }
+  LAUNCH_CHECK("gram_tcgen05_kernel");
+  // the row count travels in the same buffer (its last element), so the multi-GPU path needs ONE all-reduce
+  const size_t n = static_cast<size_t>(l.n_tiles) * kGramTileElems;
+  gram_reduce_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(g.partial, l.n_tiles, l.n_ranges, Dx, Dy, gram, gram + na,
+                                                                        gram + na + nb + Dz, static_cast<double>(rows));
+  LAUNCH_CHECK("gram_reduce_kernel");
   return 0;
 }
 

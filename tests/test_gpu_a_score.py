@@ -61,3 +61,33 @@ def test_folder_driver_mirrors_compute_py(tmp_path, a_gold):
     assert set(res) == {"dino", "openclip"}                 # load failure -> skipped, like compute.py:44-46
     for k, v in res.items():
         assert abs(v - a_gold["small"][k]["result"]) < TOL
+
+
+@pytest.mark.parametrize("n,x,y,D", [(3, 576, 576, 1024), (3, 576, 256, 1024), (2, 256, 576, 4096), (5, 130, 700, 512),
+                                     (4, 1, 1, 320), (3, 577, 129, 384), (2, 100, 1500, 1024)])
+def test_a_pairs_bf16_single_pass_kernel(n, x, y, D):
+    """bf16 features with D > 256 take the one-pass kernel (norms from the GEMM's own shared-memory tiles, ascore.cuh):
+    ragged tiles on both sides, every BN instance (y = 576 -> 192, 256 -> 128/256, 700 -> 128 ...), zero rows."""
+    g = torch.Generator().manual_seed(n * 1000 + x + y)
+    o = (torch.randn(n, x, D, generator=g) * (0.2 + torch.rand(n, x, 1, generator=g))).bfloat16()
+    r = (torch.randn(n, y, D, generator=g) + 0.3 * torch.randn(n, 1, D, generator=g)).bfloat16()
+    if x > 5:
+        o[0, 5] = 0
+    got = A.a_score_pairs(o.cuda(), r.cuda()).cpu()
+    want = torch.tensor([ao.a_pair(o[i].float(), r[i].float()) for i in range(n)])
+    assert (got.double() - want.double()).abs().max() < TOL
+
+
+def test_a_pairs_bf16_single_pass_many_pairs_persistent_loop():
+    """More pairs than SMs: every CTA walks several pairs (scale buffers alternate by pair parity); bitwise repeatable and
+    independent of how the pairs are batched."""
+    g = torch.Generator().manual_seed(77)
+    n, x, y, D = 700, 150, 200, 320
+    o = torch.randn(n, x, D, generator=g).bfloat16().cuda()
+    r = (0.5 * o[:, :1].float().cpu() + torch.randn(n, y, D, generator=g)).bfloat16().cuda()
+    a1, a2 = A.a_score_pairs(o, r), A.a_score_pairs(o, r)
+    assert torch.equal(a1, a2)
+    assert torch.equal(a1[100:433], A.a_score_pairs(o[100:433], r[100:433]))
+    idx = [0, 147, 148, 149, 699]
+    want = torch.tensor([ao.a_pair(o[i].float().cpu(), r[i].float().cpu()) for i in idx])
+    assert (a1[idx].cpu().double() - want.double()).abs().max() < TOL

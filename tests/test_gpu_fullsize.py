@@ -64,7 +64,9 @@ def test_linear_cka_c3_size_properties():
     # shards add up: two halves accumulated into one Gram == one pass
     gram, n1, dx, dy = CK.cka_gram(X[: rows // 2], Y[: rows // 2])
     gram, n2, _, _ = CK.cka_gram(X[rows // 2:], Y[rows // 2:], gram=gram)
-    assert abs(CK.cka_from_gram(gram, n1 + n2, dx, dy) - whole) < 1e-9
+    # run boundaries differ between the sharded and the unsharded job and runs are summed in fp32 registers (gram.cuh):
+    # ~1e-8 on CKA (measured 3e-8), three orders below the 1e-5 tolerance
+    assert abs(CK.cka_from_gram(gram, n1 + n2, dx, dy) - whole) < 1e-6
     Z = torch.randn(rows // 8, D, generator=g, device="cuda").to(torch.bfloat16)
     assert CK.linear_cka(X[: rows // 8], Z) < 0.01       # independent features
 
