@@ -73,6 +73,9 @@ typedef struct {
   int32_t patch_k_padded;    /* 3*patch*patch rounded up to a multiple of 64 (im2col K) */
   int32_t operand_dtype;     /* LOVR_DT_BF16 or LOVR_DT_F16: 16-bit format of the tensor-core operands (activations AND
                                 the weight matrices below); accumulation, residual stream, LayerNorm, softmax are fp32 */
+  int32_t ln_fold;           /* 1: the encoder layers' LayerNorms are folded into the qkv / fc1 GEMMs (no LayerNorm kernel):
+                                qkv_w / fc1_w hold W diag(gamma), qkv_b / fc1_b hold W beta + b and qkv_cw / fc1_cw the row
+                                sums of the folded weights — all three produced by lovr_ln_fold_weights(); ln1_* / ln2_* unused */
 } lovr_tower_config;
 
 typedef struct {
@@ -88,6 +91,8 @@ typedef struct {
   const void* fc2_w;  /* 16-bit [D, I] */
   const float* fc2_b;
   const float* ls2;   /* [D] or NULL */
+  const float* qkv_cw; /* [3D] (ln_fold) */
+  const float* fc1_cw; /* [I]  (ln_fold) */
 } lovr_layer_weights;
 
 typedef struct {
@@ -124,6 +129,19 @@ int lovr_tower_forward(lovr_tower_t* t, const void* pixels, int32_t pixel_dtype,
 int lovr_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int32_t M,
                    int32_t N, int32_t K, int32_t epi, int32_t act, int32_t operand_dtype, const float* bias,
                    const float* colscale, void* stream);
+/* LayerNorm folded into the GEMMs on both sides of it:  LN(x) W^T + b = rstd (x^ W'^T - mu cw) + bw.
+ * lovr_ln_fold_weights (weight ingest, once): W [N,K] fp32, gamma/beta [K], bias [N] or NULL ->
+ *   W16 = 16-bit(W diag(gamma)), cw[j] = sum_k W16[j,k] (of the rounded values), bw = W beta + bias.
+ * lovr_gemm_lnfold, LOVR_EPI_BF16: A = x^ (16-bit copy of the residual stream [M, ln_cols]), W = W16, bias = bw; ln_stats
+ *   [M][ln_cols/128][4] = per 128 columns of x (shift, sum(x-shift), sum((x-shift)^2), 0); C 16-bit = act(LN(x) W^T + b).
+ * lovr_gemm_lnfold, LOVR_EPI_RESID_F32: C fp32 += colscale*(acc+bias) as lovr_gemm_bf16, and additionally writes the 16-bit
+ *   copy of the updated C to xhat_out (row stride ld_xhat) and its statistics slots to stats_out [M][N/128][4]. */
+int lovr_ln_fold_weights(const float* W, const float* gamma, const float* beta, const float* bias, int32_t N, int32_t K,
+                         int32_t operand_dtype, void* W16, float* cw, float* bw, void* stream);
+int lovr_gemm_lnfold(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int32_t M, int32_t N,
+                     int32_t K, int32_t epi, int32_t act, int32_t operand_dtype, const float* bias, const float* colscale,
+                     const float* ln_stats, const float* ln_cw, int32_t ln_cols, float ln_eps, float* stats_out,
+                     void* xhat_out, int64_t ld_xhat, void* stream);
 int lovr_layernorm_bf16(const float* x, const float* gamma, const float* beta, float eps, void* y_16bit,
                         int64_t rows, int32_t D, int32_t operand_dtype, void* stream);
 /* qkv 16-bit [n_img*T, 3*H*64] -> out 16-bit [n_img*T, H*64]; softmax(q k^T / 8) v per (image, head) */

@@ -23,7 +23,7 @@ PIX_HF_RESCALE_NORMALIZE, PIX_CSCORE = 0, 1
 EXPORTS = [
     "lovr_abi_version", "lovr_last_error", "lovr_launch_count", "lovr_prof_enable", "lovr_prof_read", "lovr_prof_read_kinds",
     "lovr_tower_workspace_bytes", "lovr_tower_create", "lovr_tower_destroy", "lovr_tower_forward",
-    "lovr_gemm_bf16", "lovr_layernorm_bf16", "lovr_attention", "lovr_im2col",
+    "lovr_gemm_bf16", "lovr_gemm_lnfold", "lovr_ln_fold_weights", "lovr_layernorm_bf16", "lovr_attention", "lovr_im2col",
     "lovr_a_score_workspace_bytes", "lovr_a_score_maxcos",
     "lovr_c_score_workspace_bytes", "lovr_c_score_flow", "lovr_c_score_keypoints", "lovr_pck",
     "lovr_c_score_mutual_nn_workspace_bytes", "lovr_c_score_mutual_nn", "lovr_c_score_concat_two",
@@ -35,12 +35,12 @@ EXPORTS = [
 class TowerConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("hidden_size", "intermediate_size", "num_layers", "num_heads", "image_size",
                                          "patch_size", "act", "has_cls", "pre_ln", "layerscale")] + \
-               [("ln_eps", C.c_float), ("patch_k_padded", C.c_int32), ("operand_dtype", C.c_int32)]
+               [("ln_eps", C.c_float), ("patch_k_padded", C.c_int32), ("operand_dtype", C.c_int32), ("ln_fold", C.c_int32)]
 
 
 class LayerWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("ln1_w", "ln1_b", "qkv_w", "qkv_b", "o_w", "o_b", "ls1", "ln2_w", "ln2_b",
-                                          "fc1_w", "fc1_b", "fc2_w", "fc2_b", "ls2")]
+                                          "fc1_w", "fc1_b", "fc2_w", "fc2_b", "ls2", "qkv_cw", "fc1_cw")]
 
 
 class TowerWeights(C.Structure):
@@ -91,6 +91,11 @@ def lib():
     L.lovr_tower_forward.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32, i64, i64, i32, vp]
     L.lovr_gemm_bf16.restype = C.c_int
     L.lovr_gemm_bf16.argtypes = [vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, i32, i32, vp, vp, vp]
+    L.lovr_gemm_lnfold.restype = C.c_int
+    L.lovr_gemm_lnfold.argtypes = [vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, i32, f32, vp, vp,
+                                   i64, vp]
+    L.lovr_ln_fold_weights.restype = C.c_int
+    L.lovr_ln_fold_weights.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp]
     L.lovr_layernorm_bf16.restype = C.c_int
     L.lovr_layernorm_bf16.argtypes = [vp, vp, vp, f32, vp, i64, i32, i32, vp]
     L.lovr_attention.restype = C.c_int

@@ -46,7 +46,45 @@ struct GemmArgs {
   void* c_ptr;            // EPI_RESID_F32: base of C (fp32), row stride ldc elements, batch stride c_batch_stride
   long long ldc;
   long long c_batch_stride;
+  // ---- LayerNorm folded into the GEMMs around it (no LayerNorm kernel, no second pass over the residual stream):
+  //   LN(x) W^T + b  =  rstd (x^ W'^T - mu cw) + bw,   W' = W diag(gamma) (16-bit), cw = row sums of W', bw = W beta + b
+  // consumer (EPI_BF16; A = x^, the 16-bit copy of the residual stream, W = W', bias = bw):
+  const float* ln_stats;  // [M][N_x / 128][4] per-row partial statistics of x or nullptr (see kLnPartCols)
+  const float* ln_cw;     // [N]
+  int ln_parts;           // N_x / 128
+  float ln_eps;
+  // producer (EPI_RESID_F32): besides the fp32 update of x also emit x^ and the partial statistics of the new x
+  float* stats_out;       // [M][N / 128][4] or nullptr
+  void* xhat_out;         // 16-bit [M, N], row stride ld_xhat elements, or nullptr
+  long long ld_xhat;
 };
+
+// Row statistics travel as one slot per 128 columns: (shift, sum(x - shift), sum((x - shift)^2), unused) with shift = the
+// slot's first element — sums about a value inside the data instead of about zero, so the variance does not cancel when a
+// row has a large mean; slots are merged with the pairwise (Chan) update.
+constexpr int kLnPartCols = 128;
+
+__device__ __forceinline__ void ln_row_scales(const GemmArgs& p, int row, float& rs, float& rm) {
+  rs = 1.0f;
+  rm = 0.0f;
+  if (p.ln_stats == nullptr) return;
+  const float4* st = reinterpret_cast<const float4*>(p.ln_stats) + static_cast<size_t>(row) * p.ln_parts;
+  float n = 0.f, mean = 0.f, m2 = 0.f;
+  for (int q = 0; q < p.ln_parts; ++q) {
+    const float4 v = __ldg(st + q);
+    const float nb = static_cast<float>(kLnPartCols);
+    const float mb = v.x + v.y * (1.0f / nb);
+    const float m2b = v.z - v.y * v.y * (1.0f / nb);
+    const float delta = mb - mean;
+    const float nn = n + nb;
+    mean += delta * (nb / nn);
+    m2 += m2b + delta * delta * (n * nb / nn);
+    n = nn;
+  }
+  const float rstd = rsqrtf(m2 / n + p.ln_eps);
+  rs = rstd;
+  rm = -rstd * mean;
+}
 
 template <int BN>
 struct GemmSmem {
@@ -105,6 +143,9 @@ __device__ __forceinline__ void epilogue_tile(const uint32_t t_row, const int co
                                               float& run_max) {
     if constexpr (EPI == EPI_BF16) {
       constexpr int CH = 64;
+      // folded LayerNorm: x = rs * acc + (rm * cw + bias); without it rs = 1, rm = 0 and the result is acc + bias exactly
+      float rs, rm;
+      ln_row_scales(p, min(row0 + lane, p.M - 1), rs, rm);
 #pragma unroll 1
       for (int c = 0; c < BN / CH; ++c, ++g) {
         uint32_t r0[32], r1[32];
@@ -124,11 +165,17 @@ __device__ __forceinline__ void epilogue_tile(const uint32_t t_row, const int co
             b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j * 8));
             b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j * 8 + 4));
           }
+          float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
+          if (p.ln_cw) {
+            w0 = __ldg(reinterpret_cast<const float4*>(p.ln_cw + col0 + j * 8));
+            w1 = __ldg(reinterpret_cast<const float4*>(p.ln_cw + col0 + j * 8 + 4));
+          }
           const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const int cc = j * 8 + e;
-            const float x = __uint_as_float(cc < 32 ? r0[cc] : r1[cc - 32]) + bb[e];
+            const float x = fmaf(rs, __uint_as_float(cc < 32 ? r0[cc] : r1[cc - 32]), fmaf(rm, ww[e], bb[e]));
             v[e] = apply_act<ACT>(x);
           }
           st_shared_v4(buf_row + ((j ^ row_sw) << 4), pack16x2<F16>(v[0], v[1]), pack16x2<F16>(v[2], v[3]),
@@ -198,6 +245,8 @@ __device__ __forceinline__ void epilogue_tile(const uint32_t t_row, const int co
           tma_load_3d(buf, &tmC, &my_rbar[gi % RB], col_tile + i * CH, row0, b);
         }
       }
+      float st_shift = 0.f, st_s1 = 0.f, st_s2 = 0.f;
+      const bool row_ok = row0 + lane < p.M;
 #pragma unroll 1
       for (int c = 0; c < NCH; ++c, ++g) {
         uint32_t r0[32];
@@ -215,6 +264,7 @@ __device__ __forceinline__ void epilogue_tile(const uint32_t t_row, const int co
         tmem_ld_wait();
         const int col0 = col_tile + c * CH;
         const uint32_t buf_row = smem_u32(buf) + lane * 128;
+        uint32_t xh[16];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           uint32_t q0, q1, q2, q3;
@@ -230,12 +280,35 @@ __device__ __forceinline__ void epilogue_tile(const uint32_t t_row, const int co
           for (int e = 0; e < 4; ++e) res[e] += (__uint_as_float(r0[j * 4 + e]) + bb[e]) * ss[e];
           st_shared_v4(addr, __float_as_uint(res[0]), __float_as_uint(res[1]), __float_as_uint(res[2]),
                        __float_as_uint(res[3]));
+          if (p.stats_out != nullptr) {  // (warp-uniform) statistics of the NEW residual row for the next folded LayerNorm
+            if ((c & 3) == 0 && j == 0) st_shift = res[0];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float d = res[e] - st_shift;
+              st_s1 += d;
+              st_s2 = fmaf(d, d, st_s2);
+            }
+            xh[2 * j] = pack16x2<F16>(res[0], res[1]);
+            xh[2 * j + 1] = pack16x2<F16>(res[2], res[3]);
+          }
         }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
           tma_store_3d(&tmC, buf, col0, row0, b);
           tma_store_commit();
+        }
+        if (p.stats_out != nullptr && row_ok) {
+          // x^: this thread's 32 consecutive 16-bit values (64 contiguous bytes, whole 32-byte sectors)
+          uint4* dst = reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.xhat_out) + static_cast<size_t>(row0 + lane) * p.ld_xhat + col0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) dst[q] = make_uint4(xh[4 * q], xh[4 * q + 1], xh[4 * q + 2], xh[4 * q + 3]);
+          if ((c & 3) == 3) {  // 128 columns done: one slot
+            reinterpret_cast<float4*>(p.stats_out)[static_cast<size_t>(row0 + lane) * (p.N / kLnPartCols) + col0 / kLnPartCols] =
+                make_float4(st_shift, st_s1, st_s2, 0.f);
+            st_s1 = 0.f;
+            st_s2 = 0.f;
+          }
         }
       }
     // (A variant that replaced the TMA load/store of the residual chunk by a coalesced ld.global/st.global pass through

@@ -17,7 +17,8 @@
 // the eight epilogue warps (128 values per thread), which are written out once per unit as fp32 partials — 144 x 128 KB
 // instead of round 1's one partial per 2048 rows (1.5 GB written and re-read per 262k rows).  Partials and column sums are
 // reduced in fp64.
-//   warp 0        TMA producer: per 64-row k-block 2 boxes of the A features and 4 boxes of the B features (48 KB stage)
+//   warp 0        TMA producer: per 64-row k-block one 3-D box {64 features, 64 rows, 2 groups} for A and one with 4 groups
+//                 for B (the features are addressed as [group of 64][row][64]): 48 KB per stage
 //   warp 1        MMA issuer: 128 x 256 x 16, A and B MN-major, two TMEM accumulators (ping-pong between runs)
 //   warps 4..7    column sums of the A features (only in the unit that owns them: j == i / 2), fp32 per run, fp64 atomics
 //   warps 8..15   epilogue (warp % 4 = TMEM lane quarter, (warp - 8) / 4 = column half)
@@ -29,6 +30,8 @@ namespace lovr {
 
 constexpr int kGramChunk = 2048;
 constexpr int kGramStages = 4;
+constexpr int kGramPrefetch = 0;     // k-blocks of L2 prefetch ahead of the TMA loads: measured slower (0: 5.07 ms, 4: 5.86, 12: 6.06 at 1.2M rows)
+constexpr int kGramPaceWindow = 2;   // runs (2048 rows) a CTA may lead the slowest CTA of its range by
 constexpr int kGramThreads = 16 * 32;
 constexpr int kGramABytes = 128 * 64 * 2;
 constexpr int kGramStageBytes = (128 + 256) * 64 * 2;
@@ -41,6 +44,9 @@ struct GramArgs {
   int n_tiles, n_ranges, total_chunks;
   float* partial;   // [n_ranges * n_tiles][128][256]
   double* colsum;   // [Dx + Dy], accumulated with atomics
+  int debug;        // LOVR_GRAM_DEBUG: 1 = print per-unit cycle counts, 2 / 4 = timing experiments (see below)
+  int prefetch;     // k-blocks of L2 prefetch ahead of the TMA loads
+  int* pace;        // [n_ranges][chunks per range] arrival counters of the pacing window, zeroed per launch, or nullptr
 };
 
 __host__ __device__ inline int gram_tile_count(int Dz) {
@@ -64,7 +70,8 @@ __host__ __device__ inline void gram_tile_ij(int t, int Dz, int* i_out, int* j_o
 }
 
 __global__ void __launch_bounds__(kGramThreads, 1)
-gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, const GramArgs p) {
+gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmXa, const __grid_constant__ CUtensorMap tmXb,
+                    const __grid_constant__ CUtensorMap tmYa, const __grid_constant__ CUtensorMap tmYb, const GramArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;
@@ -81,8 +88,10 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   constexpr int kKb = kGramChunk / 64;  // k-blocks per accumulation run
 
   if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmX);
-    tma_prefetch_desc(&tmY);
+    tma_prefetch_desc(&tmXa);
+    tma_prefetch_desc(&tmXb);
+    tma_prefetch_desc(&tmYa);
+    tma_prefetch_desc(&tmYb);
     for (int i = 0; i < kGramStages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1 + 4);  // tcgen05.commit + the four column-sum warps
@@ -121,29 +130,64 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           int c0, c1, ti, tj;
           unit_chunks(u, &c0, &c1, &ti, &tj);
           const int acol = ti * 128, bcol = tj * 256;
-          const CUtensorMap* ma = acol < p.Dx ? &tmX : &tmY;
-          const CUtensorMap* mb = bcol < p.Dx ? &tmX : &tmY;
-          const int ac = acol < p.Dx ? acol : acol - p.Dx, bc = bcol < p.Dx ? bcol : bcol - p.Dx;
-          for (int c = c0; c < c1; ++c)
+          const CUtensorMap* ma = acol < p.Dx ? &tmXa : &tmYa;      // box: 2 groups of 64 features
+          const CUtensorMap* mb = bcol < p.Dx ? &tmXb : &tmYb;      // box: 4 groups
+          const int ag = (acol < p.Dx ? acol : acol - p.Dx) / 64, bg = (bcol < p.Dx ? bcol : bcol - p.Dx) / 64;
+          const int row_end = c1 * kGramChunk;
+          // Pacing window.  The CTAs of a range stream the same rows, and each row window is meant to come from HBM once and
+          // from L2 for the other ~70 CTAs.  Nothing holds the pack together: over the 1400 runs of a C3-sized job the CTAs
+          // drift apart by more rows than L2 holds and every tile ends up streaming its own copy from HBM (measured: 2.3x
+          // slower than the same kernel on a fifth of the rows).  So a CTA may start run lc only when every CTA of its range
+          // has issued run lc - kGramPaceWindow: one atomic and one polled load per 2048 rows.  (Needs one unit per CTA, all
+          // CTAs resident: the host enables it only then.)
+          int* pace = p.pace ? p.pace + (u / p.n_tiles) * ((p.total_chunks + p.n_ranges - 1) / p.n_ranges + 1) : nullptr;
+          for (int c = c0; c < c1; ++c) {
+            if (pace != nullptr && c - c0 >= kGramPaceWindow) {
+              const int* slot = pace + (c - c0 - kGramPaceWindow);
+              int seen;
+              const long long t0 = clock64();
+              for (;;) {
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(slot) : "memory");
+                if (seen >= p.n_tiles) break;
+                __nanosleep(200);
+                if (clock64() - t0 > LOVR_SPIN_LIMIT_CYCLES) {
+                  printf("lovr: gram pacing window timed out (unit %d run %d: %d of %d)\n", u, c - c0, seen, p.n_tiles);
+                  __trap();
+                }
+              }
+            }
             for (int kb = 0; kb < kKb; ++kb) {
+              const int row = c * kGramChunk + kb * 64;
+              // the CTAs that lead the pack touch rows nobody has read yet: ask L2 for them kGramPrefetch k-blocks ahead
+              const int prow = row + p.prefetch * 64;
+              if (p.prefetch > 0 && prow < row_end) {
+                tma_prefetch_3d(ma, 0, prow, ag);
+                tma_prefetch_3d(mb, 0, prow, bg);
+              }
               mbar_wait(&empty_bar[stage], phase ^ 1);
               uint8_t* sa = stage_base + stage * kGramStageBytes;
-              const int row = c * kGramChunk + kb * 64;
+              if (p.debug & 2) {  // timing experiment: no loads, the MMA runs on whatever is in shared memory
+                mbar_arrive(&full_bar[stage]);
+                if (++stage == kGramStages) { stage = 0; phase ^= 1; }
+                continue;
+              }
               mbar_arrive_expect_tx(&full_bar[stage], kGramStageBytes);
-#pragma unroll
-              for (int g = 0; g < 2; ++g) tma_load_3d(sa + g * 8192, ma, &full_bar[stage], ac + g * 64, row, 0);
-#pragma unroll
-              for (int g = 0; g < 4; ++g) tma_load_3d(sa + kGramABytes + g * 8192, mb, &full_bar[stage], bc + g * 64, row, 0);
+              tma_load_3d(sa, ma, &full_bar[stage], 0, row, ag);
+              tma_load_3d(sa + kGramABytes, mb, &full_bar[stage], 0, row, bg);
               if (++stage == kGramStages) { stage = 0; phase ^= 1; }
             }
+            if (pace != nullptr) atomicAdd(pace + (c - c0), 1);
+          }
         }
       }
     } else if (warp == 1) {
       // ===================================================================== MMA issuer
       constexpr uint32_t kDescHi = smem_desc_hi_sw128(1024);               // SBO: 8-row (K) groups 1 KB apart
-      constexpr uint32_t kIdesc = make_idesc_16(128, 256, 1, 1, false);    // A and B MN-major, bf16, fp32 accumulate
-      const uint32_t a_lo0 = smem_desc_lo(smem_u32(stage_base), 8192);     // LBO: 64-feature groups 8 KB apart
-      const uint32_t b_lo0 = smem_desc_lo(smem_u32(stage_base) + kGramABytes, 8192);
+      // (debug & 4: timing experiment with K-major descriptors on the same bytes — wrong results, same traffic)
+      const uint32_t kIdesc = (p.debug & 4) ? make_idesc_16(128, 256, 0, 0, false) : make_idesc_16(128, 256, 1, 1, false);
+      const uint32_t a_lo0 = smem_desc_lo(smem_u32(stage_base), (p.debug & 4) ? 16 : 8192);     // LBO: 64-feature groups 8 KB apart
+      const uint32_t b_lo0 = smem_desc_lo(smem_u32(stage_base) + kGramABytes, (p.debug & 4) ? 16 : 8192);
+      const uint32_t kstep = (p.debug & 4) ? 2 : (2048 >> 4);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int u = blockIdx.x; u < units; u += gridDim.x) {
@@ -161,7 +205,7 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
               const uint32_t b_lo = b_lo0 + stage * (kGramStageBytes >> 4);
 #pragma unroll
               for (int k = 0; k < 4; ++k)   // K = 16 rows = 2 KB further into every 64-feature group
-                umma_bf16_ss(d_tmem, smem_desc_join(kDescHi, a_lo + k * (2048 >> 4)), smem_desc_join(kDescHi, b_lo + k * (2048 >> 4)),
+                umma_bf16_ss(d_tmem, smem_desc_join(kDescHi, a_lo + k * kstep), smem_desc_join(kDescHi, b_lo + k * kstep),
                              kIdesc, (kb | k) != 0 ? 1u : 0u);
               umma_commit(&empty_bar[stage]);
               if (kb == kKb - 1) umma_commit(&tmem_full[acc]);
@@ -175,9 +219,12 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       }
     } else if (warp >= 4) {
       // ===================================================================== column sums of the A features
-      const int f = threadIdx.x - 4 * 32;       // feature within the A tile
-      const uint32_t col_off = (f >> 6) * 8192 + (f & 7) * 2;
-      const uint32_t chunk16 = (f & 63) >> 3;   // 16-byte chunk of the 128-byte row before swizzling
+      // thread = (group of 8 features, group of 8 rows): one LDS.128 per row brings 8 features; the 8 threads of an LDS
+      // phase read the 8 different 16-byte chunks of one row (conflict-free under the 128-byte swizzle)
+      const int t = threadIdx.x - 4 * 32;
+      const int fg = t & 15, rg = t >> 4;
+      const uint32_t off = (fg >> 3) * 8192 + rg * 1024;
+      const uint32_t chunk16 = fg & 7;
       int stage = 0;
       uint32_t phase = 0;
       for (int u = blockIdx.x; u < units; u += gridDim.x) {
@@ -185,23 +232,33 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         unit_chunks(u, &c0, &c1, &ti, &tj);
         const bool owner = tj == (ti >> 1);
         for (int c = c0; c < c1; ++c) {
-          float s = 0.f;
+          float s8[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) s8[e] = 0.f;
           for (int kb = 0; kb < kKb; ++kb) {
             mbar_wait(&full_bar[stage], phase);
             if (owner) {
-              const uint32_t base = smem_u32(stage_base + stage * kGramStageBytes) + col_off;
-#pragma unroll 8
-              for (int r = 0; r < 64; ++r) {
-                uint16_t h;
-                asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(base + r * 128 + ((chunk16 ^ (r & 7)) << 4)));
-                s += __uint_as_float(static_cast<uint32_t>(h) << 16);
+              const uint32_t base = smem_u32(stage_base + stage * kGramStageBytes) + off;
+#pragma unroll
+              for (int r = 0; r < 8; ++r) {
+                uint32_t w0, w1, w2, w3;
+                ld_shared_v4(base + r * 128 + ((chunk16 ^ r) << 4), w0, w1, w2, w3);
+                const uint32_t w[4] = {w0, w1, w2, w3};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  s8[2 * q] += __uint_as_float(w[q] << 16);
+                  s8[2 * q + 1] += __uint_as_float(w[q] & 0xffff0000u);
+                }
               }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[stage]);
             if (++stage == kGramStages) { stage = 0; phase ^= 1; }
           }
-          if (owner) atomicAdd(&p.colsum[ti * 128 + f], static_cast<double>(s));
+          if (owner) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) atomicAdd(&p.colsum[ti * 128 + fg * 8 + e], static_cast<double>(s8[e]));
+          }
         }
       }
     }
@@ -215,6 +272,7 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
       int c0, c1, ti, tj;
       unit_chunks(u, &c0, &c1, &ti, &tj);
+      const long long t_start = clock64();
       float sum[128];
 #pragma unroll
       for (int e = 0; e < 128; ++e) sum[e] = 0.f;
@@ -234,6 +292,11 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
+      }
+      if ((p.debug & 1) && threadIdx.x == 8 * 32) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        printf("gram unit %d tile (%d,%d) chunks %d cycles %lld sm %u\n", u, ti, tj, c1 - c0, clock64() - t_start, smid);
       }
       float4* dst = reinterpret_cast<float4*>(p.partial + (static_cast<size_t>(u) * 128 + quarter * 32 + lane) * 256 + half * 128);
 #pragma unroll

@@ -131,9 +131,9 @@ EncodeTiledFn encode_fn() {
 }
 
 // 3-D row-major tensor {dim0 (contiguous), dim1, dim2}; strides in elements; 128-byte swizzle;
-// box {box0, box1, 1}; out-of-bounds reads return zero, out-of-bounds writes are dropped.
+// box {box0, box1, box2}; out-of-bounds reads return zero, out-of-bounds writes are dropped.
 int make_tmap(CUtensorMap* m, const void* ptr, int elem_bytes, uint64_t dim0, uint64_t dim1, uint64_t dim2,
-              uint64_t stride1_elems, uint64_t stride2_elems, uint32_t box0, uint32_t box1) {
+              uint64_t stride1_elems, uint64_t stride2_elems, uint32_t box0, uint32_t box1, uint32_t box2 = 1) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(LOVR_E_CUDA, "cuTensorMapEncodeTiled entry point not found");
   if (box0 * elem_bytes != 128) return fail(LOVR_E_ARG, "tensor-map inner box must span 128 bytes");
@@ -142,7 +142,7 @@ int make_tmap(CUtensorMap* m, const void* ptr, int elem_bytes, uint64_t dim0, ui
   const CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   cuuint64_t dims[3] = {dim0, dim1, dim2};
   cuuint64_t strides[2] = {stride1_elems * elem_bytes, stride2_elems * elem_bytes};
-  cuuint32_t box[3] = {box0, box1, 1};
+  cuuint32_t box[3] = {box0, box1, box2};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(m, dt, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -294,9 +294,22 @@ int gemm_use_pairs() {
   return e ? atoi(e) : 1;
 }
 
+// LayerNorm folded into the GEMMs around it (gemm.cuh): consumer side (stats, cw, eps) for the 16-bit epilogue, producer
+// side (stats_out, xhat_out) for the residual epilogue.
+struct LnFold {
+  const float* stats = nullptr;
+  const float* cw = nullptr;
+  int parts = 0;
+  float eps = 0.f;
+  float* stats_out = nullptr;
+  void* xhat_out = nullptr;
+  int64_t ld_xhat = 0;
+};
+
 // Dense layer: A [M,K] bf16 (lda), W [N,K] bf16 (ldw), C [M,N] (ldc; bf16 or fp32 by epilogue).
 int dense_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int M, int N, int K,
-               int epi, int act, bool f16, const float* bias, const float* colscale, cudaStream_t s) {
+               int epi, int act, bool f16, const float* bias, const float* colscale, cudaStream_t s,
+               const LnFold* ln = nullptr) {
   if (N % kDenseBN) return fail(LOVR_E_ARG, "gemm: N=%d must be a multiple of %d", N, kDenseBN);
   if (M <= 0) return 0;
   CUtensorMap ta, tb, tc;
@@ -314,6 +327,15 @@ int dense_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, 
   g.bias = bias; g.colscale = colscale; g.rowscale = nullptr; g.rowmax = nullptr; g.n_valid = N; g.scale_ld = 0;
   g.c_ptr = C; g.ldc = ldc; g.c_batch_stride = 0;
   if (epi == lovr::EPI_F32) g.colscale = nullptr;  // (similarity scaling is only used by the C-score path)
+  if (ln != nullptr) {
+    if (epi == lovr::EPI_BF16 && ln->stats) {
+      g.ln_stats = ln->stats; g.ln_cw = ln->cw; g.ln_parts = ln->parts; g.ln_eps = ln->eps;
+    }
+    if (epi == lovr::EPI_RESID_F32 && ln->stats_out) {
+      if (N % lovr::kLnPartCols) return fail(LOVR_E_ARG, "gemm: folded LayerNorm needs N %% 128 == 0");
+      g.stats_out = ln->stats_out; g.xhat_out = ln->xhat_out; g.ld_xhat = ln->ld_xhat;
+    }
+  }
   if (pairs) return launch_gemm2(epi, act, f16, ta, tb, tc, g, s);
   return launch_gemm(kDenseBN, epi, act, f16, ta, tb, tc, g, s);
 }
@@ -492,13 +514,15 @@ struct lovr_tower {
   float* x;      // [B*T, D] fp32 residual stream
   void* ln;      // [B*T, D] bf16: LayerNorm output / attention output
   void* big;     // [B*T, I] bf16: qkv (first 3D columns' worth) or MLP hidden; patch-embed scratch
+  void* xh;      // [B*T, D] 16-bit copy of the residual stream (cfg.ln_fold)
+  float* stats;  // [B*T, D/128, 4] row statistics of the residual stream (cfg.ln_fold)
   cudaStream_t aux_stream = nullptr;  // second half-batch (created on first use)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 namespace {
 struct WsLayout {
-  size_t x, ln, big, total;
+  size_t x, ln, big, xh, stats, total;
 };
 WsLayout ws_layout(const lovr_tower_config& c, int B) {
   const int G = c.image_size / c.patch_size;
@@ -517,6 +541,13 @@ WsLayout ws_layout(const lovr_tower_config& c, int B) {
   if (qkv > big) big = qkv;
   if (pe > big) big = pe;
   off += align_up(big, 1024) + 2048;  // slack: the second half-batch's slice starts at a 1024-aligned offset
+  l.xh = l.stats = 0;
+  if (c.ln_fold) {
+    l.xh = off;
+    off += align_up(M * c.hidden_size * 2, 1024);
+    l.stats = off;
+    off += align_up(M * (c.hidden_size / lovr::kLnPartCols) * 16, 1024);
+  }
   l.total = off;
   return l;
 }
@@ -603,6 +634,15 @@ int lovr_tower_create(lovr_tower_t** out, const lovr_tower_config* cfg, const lo
   t->x = reinterpret_cast<float*>(base + l.x);
   t->ln = base + l.ln;
   t->big = base + l.big;
+  t->xh = cfg->ln_fold ? base + l.xh : nullptr;
+  t->stats = cfg->ln_fold ? reinterpret_cast<float*>(base + l.stats) : nullptr;
+  if (cfg->ln_fold) {
+    for (int i = 0; i < cfg->num_layers; ++i)
+      if (!t->layers[i].qkv_cw || !t->layers[i].fc1_cw) {
+        delete t;
+        return fail(LOVR_E_ARG, "tower_create: ln_fold needs qkv_cw / fc1_cw for every layer (lovr_ln_fold_weights)");
+      }
+  }
   *out = t;
   return 0;
 }
@@ -625,6 +665,8 @@ struct Range {
   float* x;
   void* ln;
   void* big;
+  void* xh;
+  float* stats;
 };
 size_t dtype_bytes(int dt) { return dt == LOVR_DT_F32 ? 4 : 2; }
 
@@ -644,18 +686,19 @@ int tower_embed(lovr_tower_t* t, const Range& r, int pixel_dtype) {
     return rc;
   const int wpb = 8;
   const unsigned grid = static_cast<unsigned>((static_cast<size_t>(M) + wpb - 1) / wpb);
+  uint16_t* xh = static_cast<uint16_t*>(r.xh);
+#define LOVR_EMBED_LAUNCH(V4_)                                                                                                  \
+  do {                                                                                                                          \
+    if (f16)                                                                                                                    \
+      embed_finalize_kernel<V4_, true><<<grid, wpb * 32, 0, r.s>>>(patch_out, t->w.cls, t->w.pos, t->w.pre_ln_w, t->w.pre_ln_b, \
+                                                                   c.ln_eps, r.x, r.n, T, c.has_cls, xh, r.stats);             \
+    else                                                                                                                        \
+      embed_finalize_kernel<V4_, false><<<grid, wpb * 32, 0, r.s>>>(patch_out, t->w.cls, t->w.pos, t->w.pre_ln_w, t->w.pre_ln_b, \
+                                                                    c.ln_eps, r.x, r.n, T, c.has_cls, xh, r.stats);            \
+  } while (0)
   rc = dispatch_width(
-      D,
-      [&] {
-        embed_finalize_kernel<8><<<grid, wpb * 32, 0, r.s>>>(patch_out, t->w.cls, t->w.pos, t->w.pre_ln_w, t->w.pre_ln_b,
-                                                             c.ln_eps, r.x, r.n, T, c.has_cls);
-        return 0;
-      },
-      [&] {
-        embed_finalize_kernel<6><<<grid, wpb * 32, 0, r.s>>>(patch_out, t->w.cls, t->w.pos, t->w.pre_ln_w, t->w.pre_ln_b,
-                                                             c.ln_eps, r.x, r.n, T, c.has_cls);
-        return 0;
-      });
+      D, [&] { LOVR_EMBED_LAUNCH(8); return 0; }, [&] { LOVR_EMBED_LAUNCH(6); return 0; });
+#undef LOVR_EMBED_LAUNCH
   if (rc) return rc;
   LAUNCH_CHECK("embed_finalize_kernel");
   return 0;
@@ -669,6 +712,24 @@ int tower_layer_step(lovr_tower_t* t, const Range& r, int li, int step, int attn
   const bool f16 = c.operand_dtype == LOVR_DT_F16;
   const int M = r.n * T;
   const lovr_layer_weights& lw = t->layers[li];
+  if (c.ln_fold) {
+    // LayerNorm folded: no LayerNorm launches; the residual epilogues (steps 3, 6) and embed_finalize keep x^ and the row
+    // statistics up to date, the qkv / fc1 epilogues apply them (gemm.cuh)
+    LnFold consume, produce;
+    consume.stats = r.stats; consume.parts = D / kLnPartCols; consume.eps = c.ln_eps;
+    produce.stats_out = r.stats; produce.xhat_out = r.xh; produce.ld_xhat = D;
+    switch (step) {
+      case 0: return 0;
+      case 1: consume.cw = lw.qkv_cw;
+              return dense_gemm(r.xh, D, lw.qkv_w, D, r.big, 3 * D, M, 3 * D, D, EPI_BF16, ACT_NONE, f16, lw.qkv_b, nullptr, r.s, &consume);
+      case 2: return launch_attention(r.big, r.ln, r.n, T, c.num_heads, attn_impl, f16, r.s);
+      case 3: return dense_gemm(r.ln, D, lw.o_w, D, r.x, D, M, D, D, EPI_RESID_F32, ACT_NONE, f16, lw.o_b, lw.ls1, r.s, &produce);
+      case 4: return 0;
+      case 5: consume.cw = lw.fc1_cw;
+              return dense_gemm(r.xh, D, lw.fc1_w, D, r.big, I, M, I, D, EPI_BF16, c.act, f16, lw.fc1_b, nullptr, r.s, &consume);
+      default: return dense_gemm(r.big, I, lw.fc2_w, I, r.x, D, M, D, I, EPI_RESID_F32, ACT_NONE, f16, lw.fc2_b, lw.ls2, r.s, &produce);
+    }
+  }
   switch (step) {
     case 0: return launch_layernorm(r.x, lw.ln1_w, lw.ln1_b, c.ln_eps, r.ln, M, D, f16, r.s);
     case 1: return dense_gemm(r.ln, D, lw.qkv_w, D, r.big, 3 * D, M, 3 * D, D, EPI_BF16, ACT_NONE, f16, lw.qkv_b, nullptr, r.s);
@@ -738,6 +799,8 @@ int lovr_tower_forward(lovr_tower_t* t, const void* pixels, int32_t pixel_dtype,
     rg[i].x = t->x + static_cast<size_t>(n0) * T * D;
     rg[i].ln = static_cast<uint8_t*>(t->ln) + static_cast<size_t>(n0) * T * D * 2;
     rg[i].big = static_cast<uint8_t*>(t->big) + align_up(static_cast<size_t>(n0) * T * I * 2, 1024);
+    rg[i].xh = c.ln_fold ? static_cast<uint8_t*>(t->xh) + static_cast<size_t>(n0) * T * D * 2 : nullptr;
+    rg[i].stats = c.ln_fold ? t->stats + static_cast<size_t>(n0) * T * (D / lovr::kLnPartCols) * 4 : nullptr;
   }
   if (nr == 2) {
     CUDA_TRY(cudaEventRecord(t->ev_fork, s0));
@@ -769,6 +832,41 @@ int lovr_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void*
   if (epi != LOVR_EPI_BF16 && act != LOVR_ACT_NONE) return fail(LOVR_E_ARG, "gemm: activation only with the bf16 epilogue");
   return dense_gemm(A, lda, W, ldw, C, ldc, M, N, K, epi, act, operand_dtype == LOVR_DT_F16, bias, colscale,
                     static_cast<cudaStream_t>(stream));
+}
+
+int lovr_gemm_lnfold(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, int32_t M, int32_t N,
+                     int32_t K, int32_t epi, int32_t act, int32_t operand_dtype, const float* bias, const float* colscale,
+                     const float* ln_stats, const float* ln_cw, int32_t ln_cols, float ln_eps, float* stats_out, void* xhat_out,
+                     int64_t ld_xhat, void* stream) {
+  if (int rc = require_device()) return rc;
+  if (!A || !W || !C) return fail(LOVR_E_ARG, "gemm: null pointer");
+  if (epi != LOVR_EPI_BF16 && epi != LOVR_EPI_RESID_F32) return fail(LOVR_E_ARG, "gemm_lnfold: epilogue %d", epi);
+  if (epi != LOVR_EPI_BF16 && act != LOVR_ACT_NONE) return fail(LOVR_E_ARG, "gemm: activation only with the bf16 epilogue");
+  LnFold ln;
+  if (epi == LOVR_EPI_BF16) {
+    if (!ln_stats || !ln_cw || ln_cols <= 0 || ln_cols % lovr::kLnPartCols)
+      return fail(LOVR_E_ARG, "gemm_lnfold: the 16-bit epilogue needs ln_stats, ln_cw and ln_cols %% 128 == 0");
+    ln.stats = ln_stats; ln.cw = ln_cw; ln.parts = ln_cols / lovr::kLnPartCols; ln.eps = ln_eps;
+  } else {
+    if (!stats_out || !xhat_out) return fail(LOVR_E_ARG, "gemm_lnfold: the residual epilogue needs stats_out and xhat_out");
+    ln.stats_out = stats_out; ln.xhat_out = xhat_out; ln.ld_xhat = ld_xhat;
+  }
+  return dense_gemm(A, lda, W, ldw, C, ldc, M, N, K, epi, act, operand_dtype == LOVR_DT_F16, bias, colscale,
+                    static_cast<cudaStream_t>(stream), &ln);
+}
+
+int lovr_ln_fold_weights(const float* W, const float* gamma, const float* beta, const float* bias, int32_t N, int32_t K,
+                         int32_t operand_dtype, void* W16, float* cw, float* bw, void* stream) {
+  if (int rc = require_device()) return rc;
+  if (!W || !gamma || !beta || !W16 || !cw || !bw || N <= 0 || K <= 0) return fail(LOVR_E_ARG, "ln_fold_weights: bad argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const unsigned grid = static_cast<unsigned>((N + 7) / 8);
+  if (operand_dtype == LOVR_DT_F16)
+    lovr::ln_fold_weights_kernel<true><<<grid, 256, 0, s>>>(W, gamma, beta, bias, N, K, static_cast<uint16_t*>(W16), cw, bw);
+  else
+    lovr::ln_fold_weights_kernel<false><<<grid, 256, 0, s>>>(W, gamma, beta, bias, N, K, static_cast<uint16_t*>(W16), cw, bw);
+  LAUNCH_CHECK("ln_fold_weights_kernel");
+  return 0;
 }
 
 int lovr_layernorm_bf16(const float* x, const float* gamma, const float* beta, float eps, void* y, int64_t rows,
@@ -851,7 +949,7 @@ int lovr_a_score_maxcos(const void* other, const void* ref, int32_t dtype, int64
   // bf16 features: the `other` norms come out of the shared-memory tiles of the GEMM itself (ascore.cuh), so `other` is read
   // from HBM once; only `ref` gets a norm pre-pass.  Needs more k-blocks than pipeline stages (its barrier-phase argument).
   static const int fuse_env = [] { const char* e = getenv("LOVR_A_SCORE_FUSED"); return e ? atoi(e) : 1; }();
-  if (dtype == LOVR_DT_BF16 && fuse_env && D / kBK > kAsStages) {
+  if (dtype == LOVR_DT_BF16 && fuse_env && D / kBK > 4) {
     rownorm_inv_bf16_kernel<<<static_cast<unsigned>((rows_r + wpb - 1) / wpb), wpb * 32, 0, s>>>(
         static_cast<const __nv_bfloat16*>(ref), inv_r, rows_r, D);
     LAUNCH_CHECK("rownorm_inv_bf16_kernel");
@@ -867,6 +965,7 @@ int lovr_a_score_maxcos(const void* other, const void* ref, int32_t dtype, int64
     if ((rc = ensure_smem(kern, smem))) return rc;
     AScoreArgs a{};
     a.x = x; a.y = y; a.K = D; a.n_pairs = static_cast<int>(n_pairs); a.inv_ref = inv_r; a.rowmax = rowmax;
+    { const char* e = getenv("LOVR_A_PREFETCH"); a.prefetch = e ? atoi(e) : 0; }
     const long long units = static_cast<long long>(n_pairs) * ((x + kBM - 1) / kBM);
     const int grid = units < device_info().sms ? static_cast<int>(units) : device_info().sms;
     {
@@ -1166,7 +1265,7 @@ namespace {
 // One wave of persistent CTAs: unit = (row range, upper-triangle tile of the [X|Y] Gram), see gram.cuh.  The layout depends
 // only on the sizes (148 SMs assumed for the range count; any grid size runs it correctly).
 struct CkaLayout {
-  size_t total;
+  size_t pace, pace_bytes, total;
   int n_tiles, n_ranges, total_chunks;
 };
 CkaLayout cka_layout(int64_t R, int Dx, int Dy) {
@@ -1176,7 +1275,9 @@ CkaLayout cka_layout(int64_t R, int Dx, int Dy) {
   l.n_ranges = 148 / l.n_tiles;
   if (l.n_ranges < 1) l.n_ranges = 1;
   if (l.n_ranges > l.total_chunks) l.n_ranges = l.total_chunks > 0 ? l.total_chunks : 1;
-  l.total = align_up(static_cast<size_t>(l.n_tiles) * l.n_ranges * lovr::kGramTileElems * 4, 1024);
+  l.pace = align_up(static_cast<size_t>(l.n_tiles) * l.n_ranges * lovr::kGramTileElems * 4, 1024);
+  l.pace_bytes = static_cast<size_t>(l.n_ranges) * ((l.total_chunks + l.n_ranges - 1) / l.n_ranges + 1) * 4;
+  l.total = l.pace + align_up(l.pace_bytes, 1024);
   return l;
 }
 }  // namespace
@@ -1200,21 +1301,33 @@ int lovr_cka_accumulate(const void* X, const void* Y, int64_t rows, int32_t Dx, 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int Dz = Dx + Dy;
   const size_t na = static_cast<size_t>(Dx) * Dz, nb = static_cast<size_t>(Dy) * Dy;
-  CUtensorMap tx, ty;
+  // features viewed as [groups of 64][row][64]: ONE TMA box {64 features, 64 rows, g groups} lands as g consecutive 8 KB
+  // MN-major slabs — the A operand (2 groups) and the B operand (4 groups) of a k-block are one load each
+  CUtensorMap txa, txb, tya, tyb;
   int rc;
-  if ((rc = make_tmap(&tx, X, 2, Dx, rows, 1, Dx, static_cast<uint64_t>(Dx) * rows, 64, 64))) return rc;
-  if ((rc = make_tmap(&ty, Y, 2, Dy, rows, 1, Dy, static_cast<uint64_t>(Dy) * rows, 64, 64))) return rc;
+  if ((rc = make_tmap(&txa, X, 2, 64, rows, Dx / 64, Dx, 64, 64, 64, 2))) return rc;
+  if ((rc = make_tmap(&txb, X, 2, 64, rows, Dx / 64, Dx, 64, 64, 64, 4))) return rc;
+  if ((rc = make_tmap(&tya, Y, 2, 64, rows, Dy / 64, Dy, 64, 64, 64, 2))) return rc;
+  if ((rc = make_tmap(&tyb, Y, 2, 64, rows, Dy / 64, Dy, 64, 64, 64, 4))) return rc;
   GramArgs g{};
   g.R = rows; g.Dx = Dx; g.Dy = Dy; g.n_tiles = l.n_tiles; g.n_ranges = l.n_ranges; g.total_chunks = l.total_chunks;
   g.partial = static_cast<float*>(workspace);
   g.colsum = gram + na + nb;
+  { const char* e = getenv("LOVR_GRAM_DEBUG"); g.debug = e ? atoi(e) : 0; }
+  { const char* e = getenv("LOVR_GRAM_PREFETCH"); g.prefetch = e ? atoi(e) : kGramPrefetch; }
   if ((rc = ensure_smem(reinterpret_cast<const void*>(gram_tcgen05_kernel), kGramSmem))) return rc;
   const int units = l.n_tiles * l.n_ranges;
   const int grid = units < device_info().sms ? units : device_info().sms;
+  g.pace = nullptr;
+  static const int pace_env = [] { const char* e = getenv("LOVR_GRAM_PACE"); return e ? atoi(e) : 1; }();
+  if (pace_env && units <= grid) {  // one unit per CTA, every CTA resident (1 CTA per SM by shared memory): the window cannot deadlock
+    g.pace = reinterpret_cast<int*>(static_cast<uint8_t*>(workspace) + l.pace);
+    CUDA_TRY(cudaMemsetAsync(g.pace, 0, l.pace_bytes, s));
+  }
   {
     // executed FLOPs: only the upper-triangle tiles (the algorithmic count of SURVEY.md §8d is 2 R (Dx Dz + Dy^2))
     ProfScope prof_scope(s, LOVR_PROF_OTHER, 2.0 * static_cast<double>(rows) * l.n_tiles * kGramTileElems);
-    gram_tcgen05_kernel<<<grid, kGramThreads, kGramSmem, s>>>(tx, ty, g);
+    gram_tcgen05_kernel<<<grid, kGramThreads, kGramSmem, s>>>(txa, txb, tya, tyb, g);
   }
   LAUNCH_CHECK("gram_tcgen05_kernel");
   // the row count travels in the same buffer (its last element), so the multi-GPU path needs ONE all-reduce

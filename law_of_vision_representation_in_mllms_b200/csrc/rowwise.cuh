@@ -94,11 +94,13 @@ __device__ __forceinline__ void warp_layernorm(float (&v)[V4 * 4], const float* 
 }
 
 // x[n*T + t, :] = (t is cls ? cls : patch[n*(T-has_cls) + t - has_cls, :]) + pos[t, :]; optional pre-LN.
-template <int V4>
+// With LayerNorm folding (xhat != nullptr) the row also leaves as its 16-bit copy x^ and as one statistics slot per 128
+// columns (shift, sum(x - shift), sum((x - shift)^2), 0) — the inputs of layer 0's folded LayerNorm (gemm.cuh).
+template <int V4, bool F16>
 __global__ void embed_finalize_kernel(const float* __restrict__ patch, const float* __restrict__ cls,
                                       const float* __restrict__ pos, const float* __restrict__ ln_w,
                                       const float* __restrict__ ln_b, float eps, float* __restrict__ x, int n_img,
-                                      int T, int has_cls) {
+                                      int T, int has_cls, uint16_t* __restrict__ xhat, float* __restrict__ stats) {
   constexpr int D = V4 * 128;
   const int lane = threadIdx.x & 31;
   const size_t row = blockIdx.x * static_cast<size_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -125,6 +127,63 @@ __global__ void embed_finalize_kernel(const float* __restrict__ patch, const flo
   for (int j = 0; j < V4; ++j)
     reinterpret_cast<float4*>(x + row * D)[j * 32 + lane] =
         make_float4(v[j * 4 + 0], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
+  if (xhat != nullptr) {
+#pragma unroll
+    for (int j = 0; j < V4; ++j) {  // vector j of every lane = columns [128 j, 128 j + 128): one statistics slot
+      uint2 o;
+      o.x = pack16x2<F16>(v[j * 4 + 0], v[j * 4 + 1]);
+      o.y = pack16x2<F16>(v[j * 4 + 2], v[j * 4 + 3]);
+      reinterpret_cast<uint2*>(xhat + row * D)[j * 32 + lane] = o;
+      const float shift = __shfl_sync(0xffffffffu, v[j * 4], 0);
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float d = v[j * 4 + e] - shift;
+        s1 += d;
+        s2 = fmaf(d, d, s2);
+      }
+      s1 = warp_sum(s1);
+      s2 = warp_sum(s2);
+      if (lane == 0) reinterpret_cast<float4*>(stats)[row * V4 + j] = make_float4(shift, s1, s2, 0.f);
+    }
+  }
+}
+
+// Weight ingest for the folded LayerNorm (once per tower): W [N, K] fp32, gamma / beta [K], bias [N] or nullptr ->
+//   W16[j, k] = 16-bit(W[j, k] * gamma[k]),   cw[j] = sum_k W16[j, k] (of the ROUNDED values: the epilogue subtracts
+//   mu * cw from x^ W16^T, which must cancel exactly),   bw[j] = sum_k W[j, k] * beta[k] + bias[j].   One warp per row j.
+template <bool F16>
+__global__ void ln_fold_weights_kernel(const float* __restrict__ W, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, const float* __restrict__ bias, int N, int K,
+                                       uint16_t* __restrict__ W16, float* __restrict__ cw, float* __restrict__ bw) {
+  const int lane = threadIdx.x & 31;
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (j >= N) return;
+  float sc = 0.f, sb = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float w = W[static_cast<size_t>(j) * K + k];
+    const float wg = w * __ldg(gamma + k);
+    float r;
+    uint16_t h;
+    if constexpr (F16) {
+      const __half hv = __float2half_rn(wg);
+      h = __half_as_ushort(hv);
+      r = __half2float(hv);
+    } else {
+      const __nv_bfloat16 hv = __float2bfloat16(wg);
+      h = __bfloat16_as_ushort(hv);
+      r = __bfloat162float(hv);
+    }
+    W16[static_cast<size_t>(j) * K + k] = h;
+    sc += r;
+    sb = fmaf(w, __ldg(beta + k), sb);
+  }
+  sc = warp_sum(sc);
+  sb = warp_sum(sb);
+  if (lane == 0) {
+    cw[j] = sc;
+    bw[j] = sb + (bias ? bias[j] : 0.f);
+  }
 }
 
 // y[row,:] (bf16) = LayerNorm(x[row,:]) * gamma + beta, fp32 statistics.

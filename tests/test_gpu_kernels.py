@@ -184,3 +184,47 @@ def test_attention_growing_logits_redo_path(dtype, T):
             got = G.attention(x, n, T, H, impl)
             assert torch.isfinite(got.float()).all()
             assert G.rel_err(got, want) < (4e-3 if dtype == torch.bfloat16 else 1e-3), (impl, T)
+
+
+@pytest.mark.parametrize("op_dtype,tol", [(torch.bfloat16, 6e-3), (torch.float16, 8e-4)])
+@pytest.mark.parametrize("M,D,row_mean", [(3 * 577, 1024, 0.0), (100, 768, 0.0), (700, 1024, 40.0)])
+def test_layernorm_folded_into_gemm_epilogues(op_dtype, tol, M, D, row_mean):
+    """LN(x) W^T + b = rstd (x^ W'^T - mu cw) + bw (gemm.cuh): the residual epilogue emits x^ and per-128-column statistics
+    slots, lovr_ln_fold_weights folds gamma / beta into the next GEMM's weights, the 16-bit epilogue applies mu / rstd.
+    Against plain torch fp32: x + GEMM, then LayerNorm, then Linear + activation.  `row_mean` = 40 puts a DC offset of 40
+    standard deviations on every row (the shifted sums keep the variance from cancelling)."""
+    g = torch.Generator().manual_seed(M + D)
+    K1, N2 = 512, 768
+    A = (torch.randn(M, K1, generator=g) * 0.5).to(op_dtype)
+    W1 = (torch.randn(D, K1, generator=g) * 0.05).to(op_dtype)
+    b1 = torch.randn(D, generator=g) * 0.1
+    ls = 0.5 + torch.rand(D, generator=g)
+    x0 = torch.randn(M, D, generator=g) + row_mean
+    x0[:, 7] += 25.0                                                    # an outlier channel
+    want_x = x0 + (A.float() @ W1.float().T + b1) * ls
+    x = x0.clone().cuda()
+    xhat, stats = G.gemm_resid_lnfold(A.cuda(), W1.cuda(), x, b1.cuda(), ls.cuda())
+    assert G.rel_err(x.cpu(), want_x) < 1e-5
+    assert torch.equal(xhat.cpu(), x.cpu().to(op_dtype))                # x^ is exactly the rounded residual stream
+    st = stats.cpu().double()                                           # slots -> row mean / variance (pairwise merge)
+    seg_mean = st[..., 0] + st[..., 1] / 128
+    seg_m2 = st[..., 2] - st[..., 1] ** 2 / 128
+    mean = seg_mean.mean(1)
+    var = (seg_m2.sum(1) + 128 * ((seg_mean - mean[:, None]) ** 2).sum(1)) / D
+    assert (mean - want_x.double().mean(1)).abs().max() < 1e-4 * (1 + abs(row_mean))
+    assert ((var - want_x.double().var(1, unbiased=False)) / want_x.double().var(1, unbiased=False)).abs().max() < 1e-4
+    # consumer
+    gamma, beta = 0.5 + torch.rand(D, generator=g), 0.2 * torch.randn(D, generator=g)
+    W2 = torch.randn(N2, D, generator=g) * 0.04
+    b2 = torch.randn(N2, generator=g) * 0.1
+    W16, cw, bw = G.ln_fold_weights(W2.cuda(), gamma.cuda(), beta.cuda(), b2.cuda(), op_dtype)
+    assert torch.equal(W16.cpu(), (W2 * gamma).to(op_dtype))
+    assert torch.allclose(cw.cpu(), W16.float().cpu().sum(1), rtol=1e-5, atol=1e-5)
+    assert torch.allclose(bw.cpu(), W2 @ beta + b2, rtol=1e-5, atol=1e-5)
+    for act, fn in ((0, lambda t: t), (1, lambda t: t * torch.sigmoid(1.702 * t))):
+        got = G.gemm_consume_lnfold(xhat, stats, W16, cw, bw, 1e-5, act).float().cpu()
+        want = fn(torch.nn.functional.layer_norm(want_x, (D,), gamma, beta, 1e-5) @ W2.T + b2)
+        rel = G.rel_err(got, want)
+        # x^ is rounded relative to |x|, not |x - mu|: a row whose mean is 40 standard deviations loses log2(40) bits of
+        # (x - mu) — the documented limit of the fold (real residual streams have |mu| < sigma); the statistics stay exact
+        assert rel < tol * (12 if row_mean else 1), (act, rel)

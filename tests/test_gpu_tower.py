@@ -45,12 +45,12 @@ def tolerance_for(name, rec):
     return 0.75 * ref if ref is not None else 1.2e-2
 
 
-def _build(case, attn_impl=_lib.ATTN_AUTO, operand_dtype="bf16"):
+def _build(case, attn_impl=_lib.ATTN_AUTO, operand_dtype="bf16", ln_fold=0):
     name, key, nl, size, n, sl, sf = case
     spec, sd, imgs = vit_case_inputs(case)
     args = types.SimpleNamespace(mm_vision_select_layer=sl, mm_vision_select_feature=sf, lovr_spec=spec,
                                  lovr_state_dict=sd, lovr_image_size=size, lovr_max_batch=4,
-                                 lovr_operand_dtype=operand_dtype, lovr_pos_interp=case_pos_interp(name))
+                                 lovr_operand_dtype=operand_dtype, lovr_pos_interp=case_pos_interp(name), lovr_ln_fold=ln_fold)
     tower = _CLS[spec.family](key, args)
     tower._attn_impl = attn_impl
     return tower, spec, sd, imgs
@@ -108,6 +108,37 @@ def test_tower_fp16_operands_meet_north_star_tolerance(case, golden_dir):
         assert rel < (0.5 * ref16 if ref16 is not None and style != "outlier" else 6e-3), (rel, ref16)
         if style == "outlier":
             assert rel_rest < 1.2e-2        # measured 7.6e-3 (CLIP; 3.7e-3 over all channels), reference fp16 path 2.8e-2
+
+
+FOLD_CASES = ["clip336_l3", "dinov2_336_l3", "siglip224_l3", "clip224_l3_clspatch", "clip336_full_hf", "dinov2_336_full_raw",
+              "siglip224_full_hf", "clip336_full_outlier", "clip336_full"]
+
+
+@pytest.mark.parametrize("cname", FOLD_CASES)
+def test_tower_with_layernorm_folded_into_the_gemms(cname, golden_dir):
+    """`lovr_ln_fold=1`: no LayerNorm kernel — the residual epilogues emit the 16-bit residual copy and row statistics, the qkv /
+    fc1 epilogues apply them (include/lovr_b200.h `ln_fold`).  Same fixtures, same bars as the unfolded path (fp16 operands:
+    1e-3 on benchmark / un-rounded weights); the CPU emulation predicts errors equal to the unfolded path on those weights and
+    ~20 % larger on the stress weights (gamma is folded into the rounded weight matrix)."""
+    case = next(c for c in VIT_CASES if c[0] == cname)
+    rec = torch.load(os.path.join(golden_dir, f"vit_{cname}.pt"))
+    launches0 = _lib.launch_count()
+    res = {}
+    for od in ("fp16", "bf16"):
+        tower, spec, sd, imgs = _build(case, operand_dtype=od, ln_fold=1)
+        out = tower(imgs.cuda())
+        assert torch.isfinite(out).all() and tuple(out.shape) == tuple(rec["shape"])
+        res[od] = G.rel_err(out[:, rec["rows"]].cpu(), rec["values"])
+    style = case_style(cname)
+    print(f"{cname} folded LayerNorm: fp16 {res['fp16']:.3e}, bf16 {res['bf16']:.3e}")
+    if style in ("hf_init", "hf_init_raw"):
+        assert res["fp16"] < REL_TOL
+    elif rec.get("ref_fp16_rel") is not None and style != "outlier":
+        assert res["fp16"] < 0.5 * rec["ref_fp16_rel"]
+    else:
+        assert res["fp16"] < 6e-3
+    assert res["bf16"] < (tolerance_for(cname, rec) if style != "stress" else 1.2 * tolerance_for(cname, rec))
+    assert _lib.launch_count() > launches0
 
 
 @pytest.mark.parametrize("cname", ["clip336_l3", "dinov2_336_l3", "siglip224_l3"])
