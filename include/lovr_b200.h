@@ -30,11 +30,11 @@ enum { LOVR_DT_F32 = 0, LOVR_DT_BF16 = 1, LOVR_DT_F16 = 2 };
 /* hidden_act of the HF config: quick_gelu (openai CLIP), gelu (OpenCLIP, DINOv2), gelu_pytorch_tanh (SigLIP) */
 enum { LOVR_ACT_NONE = 0, LOVR_ACT_QUICK_GELU = 1, LOVR_ACT_GELU_ERF = 2, LOVR_ACT_GELU_TANH = 3 };
 enum { LOVR_EPI_BF16 = 0, LOVR_EPI_RESID_F32 = 1, LOVR_EPI_F32 = 2 };
-/* attention implementations: 0 = tcgen05, one softmax pipeline per CTA; 2 = tcgen05, single-pass online softmax, two pipelines per CTA, P via shared memory; 3 = same with P via TMEM; 4 = three pipelines, P via TMEM;
- * 1 = CUDA-core cross-check used only by tests */
-enum { LOVR_ATTN_TCGEN05 = 0, LOVR_ATTN_SIMT_CHECK = 1, LOVR_ATTN_TCGEN05_V2 = 2, LOVR_ATTN_TCGEN05_V2_PTMEM = 3,
-       LOVR_ATTN_TCGEN05_V2_3PIPE = 4, LOVR_ATTN_AUTO = 5 /* the product default: currently 7 (6 when T <= 128) */,
-       LOVR_ATTN_TCGEN05_V3 = 6 /* three pipelines, register-only bookkeeping, deferred P hand-off, K/V streamed per block */,
+/* attention implementations.  Values 0, 2, 3, 4 (the first two tcgen05 generations) were removed from the build in round 2:
+ * they return LOVR_E_UNSUPPORTED.  1 = CUDA-core cross-check used only by tests. */
+enum { LOVR_ATTN_SIMT_CHECK = 1,
+       LOVR_ATTN_AUTO = 5 /* the product default: currently 7 (6 when T <= 128) */,
+       LOVR_ATTN_TCGEN05_V3 = 6 /* one CTA per (image, head): three softmax pipelines, P through TMEM, K/V streamed per block */,
        LOVR_ATTN_TCGEN05_V4 = 7 /* persistent: one CTA per SM, tiles of consecutive (image, head) items roll through the three pipelines */ };
 
 int lovr_abi_version(void);
@@ -73,9 +73,10 @@ typedef struct {
   int32_t patch_k_padded;    /* 3*patch*patch rounded up to a multiple of 64 (im2col K) */
   int32_t operand_dtype;     /* LOVR_DT_BF16 or LOVR_DT_F16: 16-bit format of the tensor-core operands (activations AND
                                 the weight matrices below); accumulation, residual stream, LayerNorm, softmax are fp32 */
-  int32_t ln_fold;           /* 1: the encoder layers' LayerNorms are folded into the qkv / fc1 GEMMs (no LayerNorm kernel):
-                                qkv_w / fc1_w hold W diag(gamma), qkv_b / fc1_b hold W beta + b and qkv_cw / fc1_cw the row
-                                sums of the folded weights — all three produced by lovr_ln_fold_weights(); ln1_* / ln2_* unused */
+  int32_t ln_fold;           /* bit mask: 1 = LayerNorm-1 folded into the qkv GEMM, 2 = LayerNorm-2 folded into fc1 (no LayerNorm
+                                kernel for a folded one): the folded GEMM's weight holds W diag(gamma), its bias W beta + b and
+                                qkv_cw / fc1_cw the row sums of the folded weight — all three produced by
+                                lovr_ln_fold_weights(); the folded LayerNorm's ln*_w / ln*_b are unused */
 } lovr_tower_config;
 
 typedef struct {
@@ -114,7 +115,7 @@ void lovr_tower_destroy(lovr_tower_t* t);
 /* pixels [n,3,R,R] in pixel_dtype (NCHW, already normalised like the HF processors do) ->
  * out[n, p, out_col_off : out_col_off + D], row stride out_ld elements, dtype out_dtype.
  * layers_to_run = select_layer mod (L+1) (hidden_states[select_layer]); drop_cls=1 for 'patch'.
- * attn_impl: LOVR_ATTN_TCGEN05 (product) or LOVR_ATTN_SIMT_CHECK (cross-check kernel for tests). */
+ * attn_impl: LOVR_ATTN_AUTO (product) or LOVR_ATTN_SIMT_CHECK (cross-check kernel for tests). */
 int lovr_tower_forward(lovr_tower_t* t, const void* pixels, int32_t pixel_dtype, int32_t n_img,
                        int32_t layers_to_run, int32_t drop_first_token, void* out, int32_t out_dtype,
                        int64_t out_ld, int64_t out_col_off, int32_t attn_impl, void* stream);

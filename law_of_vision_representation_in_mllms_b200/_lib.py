@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "liblovr_b200.so")
 OK, E_ARG, E_CUDA, E_UNSUPPORTED, E_NOMEM = 0, -1, -2, -3, -4
 DT_F32, DT_BF16, DT_F16 = 0, 1, 2
 EPI_BF16, EPI_RESID_F32, EPI_F32 = 0, 1, 2
-ATTN_TCGEN05, ATTN_SIMT_CHECK, ATTN_TCGEN05_V2, ATTN_TCGEN05_V2_PTMEM, ATTN_TCGEN05_V2_3PIPE = 0, 1, 2, 3, 4
+ATTN_SIMT_CHECK = 1
 ATTN_AUTO = 5
 ATTN_TCGEN05_V3 = 6
 ATTN_TCGEN05_V4 = 7

@@ -132,10 +132,15 @@ def pck_per_pair(pred, gt, visible, thresholds):
     B, K, _ = pred.shape
     dev = pred.device
     out = torch.empty(B, 4, dtype=torch.float32, device=dev)
+    # every device tensor whose raw pointer goes into the call is held in a local until after the launch: a temporary freed
+    # between two argument evaluations can be handed to the NEXT host-to-device copy by the caching allocator, which then
+    # overwrites it before the kernel reads it (seen on hardware: thresholds landing in gt's block changed a PCK)
     vis = visible.to(dev, torch.uint8).contiguous()
+    pred_f = pred.float().contiguous()
+    gt_f = gt.to(dev).float().contiguous()
+    thr_f = thresholds.to(dev).float().contiguous()
     with torch.cuda.device(dev):
-        _lib.check(_lib.lib().lovr_pck(_lib.ptr(pred.float().contiguous()), _lib.ptr(gt.to(dev).float().contiguous()),
-                                       _lib.ptr(vis), _lib.ptr(thresholds.to(dev).float().contiguous()), B, K,
+        _lib.check(_lib.lib().lovr_pck(_lib.ptr(pred_f), _lib.ptr(gt_f), _lib.ptr(vis), _lib.ptr(thr_f), B, K,
                                        _lib.ptr(out), _lib.stream_ptr(dev)), "lovr_pck")
     return out
 

@@ -22,7 +22,34 @@
 #pragma once
 #include <cuda_fp16.h>
 
-#include "attention2.cuh"
+#include "ptx.cuh"
+
+namespace lovr {
+
+constexpr int kAttnMaxBlocks = 5;  // T <= 640: K and V of one (image, head) stay resident in shared memory
+constexpr float kAttnRescaleLog2 = 8.0f;
+
+struct AttnArgs {
+  int T;        // tokens per image
+  int H;        // heads
+  int nb;       // ceil(T / 128)
+  int last_w;   // width of the last KV block, multiple of 32
+  int nu;       // ceil(T / 64) KV units
+  int last_w64; // width of the last 64-column unit: 32 or 64
+  float scale;  // head_dim^-0.5
+  uint16_t* out;  // [N*T, H*64], 16-bit operand format
+  long long* trace;  // debug & 8: clock64 timeline of CTA 0, pipeline 0 (diagnostics only)
+  int n_items;    // (persistent kernel) images x heads
+  int debug;      // timing experiments only (LOVR_ATTN_DEBUG)
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+}  // namespace lovr
 
 namespace lovr {
 

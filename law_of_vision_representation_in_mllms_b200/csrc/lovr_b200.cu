@@ -15,8 +15,6 @@
 #include <string>
 #include <vector>
 
-#include "attention.cuh"
-#include "attention2.cuh"
 #include "attention3.cuh"
 #include "attention4.cuh"
 #include "attention_simt.cuh"
@@ -450,31 +448,8 @@ int launch_attention(const void* qkv, void* out, int n_img, int T, int H, int im
     LAUNCH_CHECK("attention3_tcgen05_kernel");
     return 0;
   }
-  if (impl == LOVR_ATTN_TCGEN05_V2 || impl == LOVR_ATTN_TCGEN05_V2_PTMEM || impl == LOVR_ATTN_TCGEN05_V2_3PIPE) {
-    const int np = impl == LOVR_ATTN_TCGEN05_V2_3PIPE ? 3 : 2;
-    const bool pt = impl != LOVR_ATTN_TCGEN05_V2;
-    const size_t smem2 = lovr::attn2_smem_bytes(nb, np, pt);
-    const int threads = lovr::attn2_threads(np);
-#define LOVR_ATTN2_LAUNCH(F16_, PT_, NP_)                                                                             \
-  do {                                                                                                               \
-    auto kern = lovr::attention2_tcgen05_kernel<F16_, PT_, NP_>;                                                     \
-    if (int rc_ = ensure_smem(reinterpret_cast<const void*>(kern), smem2)) return rc_;                                 \
-    kern<<<n_img * H, threads, smem2, s>>>(tq, a);                                                                   \
-  } while (0)
-    if (np == 3) { if (f16) LOVR_ATTN2_LAUNCH(true, true, 3); else LOVR_ATTN2_LAUNCH(false, true, 3); }
-    else if (pt) { if (f16) LOVR_ATTN2_LAUNCH(true, true, 2); else LOVR_ATTN2_LAUNCH(false, true, 2); }
-    else { if (f16) LOVR_ATTN2_LAUNCH(true, false, 2); else LOVR_ATTN2_LAUNCH(false, false, 2); }
-#undef LOVR_ATTN2_LAUNCH
-    LAUNCH_CHECK("attention2_tcgen05_kernel");
-    return 0;
-  }
-  const size_t smem = lovr::attn_smem_bytes(nb);
-  if (int rc = ensure_smem(reinterpret_cast<const void*>(lovr::attention_tcgen05_kernel<true>), smem)) return rc;
-  if (int rc = ensure_smem(reinterpret_cast<const void*>(lovr::attention_tcgen05_kernel<false>), smem)) return rc;
-  if (f16) lovr::attention_tcgen05_kernel<true><<<n_img * H, lovr::kAttnThreads, smem, s>>>(tq, a);
-  else lovr::attention_tcgen05_kernel<false><<<n_img * H, lovr::kAttnThreads, smem, s>>>(tq, a);
-  LAUNCH_CHECK("attention_tcgen05_kernel");
-  return 0;
+  return fail(LOVR_E_UNSUPPORTED, "attention: implementation %d is not in this build (the first two tcgen05 generations were "
+                                  "removed in round 2: use LOVR_ATTN_AUTO, _V3, _V4 or LOVR_ATTN_SIMT_CHECK)", impl);
 }
 
 int launch_im2col(const void* pixels, int dt, void* cols, int n_img, int R, int P, int Kpad, bool f16, cudaStream_t s) {
@@ -638,9 +613,9 @@ int lovr_tower_create(lovr_tower_t** out, const lovr_tower_config* cfg, const lo
   t->stats = cfg->ln_fold ? reinterpret_cast<float*>(base + l.stats) : nullptr;
   if (cfg->ln_fold) {
     for (int i = 0; i < cfg->num_layers; ++i)
-      if (!t->layers[i].qkv_cw || !t->layers[i].fc1_cw) {
+      if (((cfg->ln_fold & 1) && !t->layers[i].qkv_cw) || ((cfg->ln_fold & 2) && !t->layers[i].fc1_cw)) {
         delete t;
-        return fail(LOVR_E_ARG, "tower_create: ln_fold needs qkv_cw / fc1_cw for every layer (lovr_ln_fold_weights)");
+        return fail(LOVR_E_ARG, "tower_create: ln_fold needs qkv_cw / fc1_cw for every folded LayerNorm (lovr_ln_fold_weights)");
       }
   }
   *out = t;
@@ -686,7 +661,7 @@ int tower_embed(lovr_tower_t* t, const Range& r, int pixel_dtype) {
     return rc;
   const int wpb = 8;
   const unsigned grid = static_cast<unsigned>((static_cast<size_t>(M) + wpb - 1) / wpb);
-  uint16_t* xh = static_cast<uint16_t*>(r.xh);
+  uint16_t* xh = (c.ln_fold & 1) ? static_cast<uint16_t*>(r.xh) : nullptr;
 #define LOVR_EMBED_LAUNCH(V4_)                                                                                                  \
   do {                                                                                                                          \
     if (f16)                                                                                                                    \
@@ -713,21 +688,27 @@ int tower_layer_step(lovr_tower_t* t, const Range& r, int li, int step, int attn
   const int M = r.n * T;
   const lovr_layer_weights& lw = t->layers[li];
   if (c.ln_fold) {
-    // LayerNorm folded: no LayerNorm launches; the residual epilogues (steps 3, 6) and embed_finalize keep x^ and the row
-    // statistics up to date, the qkv / fc1 epilogues apply them (gemm.cuh)
+    // LayerNorm folded into the GEMMs around it (bit 0: LN1 -> qkv, produced by fc2 / embed_finalize; bit 1: LN2 -> fc1,
+    // produced by the out-projection): the producing residual epilogue keeps x^ and the row statistics up to date, the
+    // consuming 16-bit epilogue applies them (gemm.cuh); a LayerNorm that is not folded runs as the kernel it was
+    const bool f1 = c.ln_fold & 1, f2 = c.ln_fold & 2;
     LnFold consume, produce;
     consume.stats = r.stats; consume.parts = D / kLnPartCols; consume.eps = c.ln_eps;
     produce.stats_out = r.stats; produce.xhat_out = r.xh; produce.ld_xhat = D;
     switch (step) {
-      case 0: return 0;
+      case 0: return f1 ? 0 : launch_layernorm(r.x, lw.ln1_w, lw.ln1_b, c.ln_eps, r.ln, M, D, f16, r.s);
       case 1: consume.cw = lw.qkv_cw;
-              return dense_gemm(r.xh, D, lw.qkv_w, D, r.big, 3 * D, M, 3 * D, D, EPI_BF16, ACT_NONE, f16, lw.qkv_b, nullptr, r.s, &consume);
+              return dense_gemm(f1 ? r.xh : r.ln, D, lw.qkv_w, D, r.big, 3 * D, M, 3 * D, D, EPI_BF16, ACT_NONE, f16, lw.qkv_b, nullptr,
+                                r.s, f1 ? &consume : nullptr);
       case 2: return launch_attention(r.big, r.ln, r.n, T, c.num_heads, attn_impl, f16, r.s);
-      case 3: return dense_gemm(r.ln, D, lw.o_w, D, r.x, D, M, D, D, EPI_RESID_F32, ACT_NONE, f16, lw.o_b, lw.ls1, r.s, &produce);
-      case 4: return 0;
+      case 3: return dense_gemm(r.ln, D, lw.o_w, D, r.x, D, M, D, D, EPI_RESID_F32, ACT_NONE, f16, lw.o_b, lw.ls1, r.s,
+                                f2 ? &produce : nullptr);
+      case 4: return f2 ? 0 : launch_layernorm(r.x, lw.ln2_w, lw.ln2_b, c.ln_eps, r.ln, M, D, f16, r.s);
       case 5: consume.cw = lw.fc1_cw;
-              return dense_gemm(r.xh, D, lw.fc1_w, D, r.big, I, M, I, D, EPI_BF16, c.act, f16, lw.fc1_b, nullptr, r.s, &consume);
-      default: return dense_gemm(r.big, I, lw.fc2_w, I, r.x, D, M, D, I, EPI_RESID_F32, ACT_NONE, f16, lw.fc2_b, lw.ls2, r.s, &produce);
+              return dense_gemm(f2 ? r.xh : r.ln, D, lw.fc1_w, D, r.big, I, M, I, D, EPI_BF16, c.act, f16, lw.fc1_b, nullptr, r.s,
+                                f2 ? &consume : nullptr);
+      default: return dense_gemm(r.big, I, lw.fc2_w, I, r.x, D, M, D, I, EPI_RESID_F32, ACT_NONE, f16, lw.fc2_b, lw.ls2, r.s,
+                                 f1 ? &produce : nullptr);
     }
   }
   switch (step) {

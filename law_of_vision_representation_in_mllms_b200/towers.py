@@ -34,9 +34,9 @@ DEFAULT_MAX_BATCH = int(os.environ.get("LOVR_MAX_BATCH", "128"))   # images per 
 class _NativeTower:
     """One (weights, resolution) instance of the native tower: packed device weights + workspace + handle."""
 
-    def __init__(self, spec: TowerSpec, cw, device, max_batch, operand_dtype=torch.bfloat16, ln_fold=True):
+    def __init__(self, spec: TowerSpec, cw, device, max_batch, operand_dtype=torch.bfloat16, ln_fold=0):
         self.spec = spec
-        self.ln_fold = bool(ln_fold)
+        self.ln_fold = int(ln_fold)       # bit mask: 1 = LayerNorm-1 into qkv, 2 = LayerNorm-2 into fc1
         self.operand_dtype = operand_dtype
         self.device = torch.device(device)
         self.max_batch = max_batch
@@ -58,16 +58,17 @@ class _NativeTower:
             num_heads=spec.num_heads, image_size=spec.image_size, patch_size=P, act=spec.act,
             has_cls=int(spec.has_cls), pre_ln=int(spec.pre_ln), layerscale=int(spec.layerscale),
             ln_eps=spec.ln_eps, patch_k_padded=kpad, operand_dtype=_lib.torch_dtype_code(operand_dtype),
-            ln_fold=int(self.ln_fold))
+            ln_fold=self.ln_fold)
         layers = (_lib.LayerWeights * spec.num_layers)()
         bf = operand_dtype      # 16-bit tensor-core operand format of the weight matrices
         for i, lw in enumerate(cw["layers"]):
             L = layers[i]
             folded = {}
-            if self.ln_fold:
-                # LayerNorm folded into the qkv / fc1 GEMMs (include/lovr_b200.h `ln_fold`): W diag(gamma) in the operand
-                # format, its row sums and W beta + b come from the library's own ingest kernel, from the fp32 weights
+            # LayerNorm folded into the qkv / fc1 GEMMs (include/lovr_b200.h `ln_fold`): W diag(gamma) in the operand
+            # format, its row sums and W beta + b come from the library's own ingest kernel, from the fp32 weights
+            if self.ln_fold & 1:
                 folded.update(self._fold(lw["qkv_w"], lw["ln1_w"], lw["ln1_b"], lw["qkv_b"], "qkv", bf))
+            if self.ln_fold & 2:
                 folded.update(self._fold(lw["fc1_w"], lw["ln2_w"], lw["ln2_b"], lw["fc1_b"], "fc1", bf))
             for name, dt in (("ln1_w", None), ("ln1_b", None), ("qkv_w", bf), ("qkv_b", None), ("o_w", bf),
                              ("o_b", None), ("ls1", None), ("ln2_w", None), ("ln2_b", None), ("fc1_w", bf),
@@ -188,10 +189,11 @@ class _B200VisionTower(nn.Module):
                                torch.bfloat16: torch.bfloat16, torch.float16: torch.float16}[od]
         # DINOv2 position-table interpolation form: the reference's pinned transformers (4.31/4.38, default) or this image's 5.5
         self._pos_interp = getattr(self._args, "lovr_pos_interp", os.environ.get("LOVR_DINOV2_POS_INTERP", DEFAULT_POS_INTERP))
-        # LayerNorm folding (lovr_ln_fold=1 / LOVR_LN_FOLD=1): no LayerNorm kernel, one pass less over the residual stream per
-        # LayerNorm.  Off by default: measured 3.4 % SLOWER end to end (2387 vs 2470 images/s) — the K=1024 out-projection is
-        # bound by its residual epilogue, which the fold makes heavier
-        self._ln_fold = bool(int(getattr(self._args, "lovr_ln_fold", os.environ.get("LOVR_LN_FOLD", "0"))))
+        # LayerNorm folding (lovr_ln_fold / LOVR_LN_FOLD, bit mask: 1 = LayerNorm-1 into qkv, 2 = LayerNorm-2 into fc1): a folded
+        # LayerNorm has no kernel and costs one pass less over the residual stream.  Folding both was measured 3.4 % SLOWER end
+        # to end (2387 vs 2470 images/s): the K=1024 out-projection is bound by its residual epilogue, which producing
+        # LayerNorm-2's inputs makes heavier
+        self._ln_fold = int(getattr(self._args, "lovr_ln_fold", os.environ.get("LOVR_LN_FOLD", "0")))
         self._native.clear()
         self._instance(self._default_image_size())
         self.image_processor = self._make_image_processor()

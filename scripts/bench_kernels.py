@@ -51,12 +51,7 @@ def main():
         res.append(dict(kernel=name, ms=ms, tflops=flops / ms / 1e9))
     ms = timeit(lambda: torch.matmul(A, W["fc1"].T))
     res.append(dict(kernel="torch_matmul_fc1_shape(cuBLAS)", ms=ms, tflops=2 * M * D * I / ms / 1e9))
-    ms = timeit(lambda: G.attention(qkv, n_img, T, H, _lib.ATTN_TCGEN05))
-    res.append(dict(kernel="attention_tcgen05", ms=ms, tflops=4 * n_img * H * T * T * 64 / ms / 1e9))
-    ms = timeit(lambda: G.attention(qkv, n_img, T, H, _lib.ATTN_TCGEN05_V2))
-    res.append(dict(kernel="attention2_tcgen05", ms=ms, tflops=4 * n_img * H * T * T * 64 / ms / 1e9))
-    for impl, nm in ((_lib.ATTN_TCGEN05_V2_PTMEM, "attention2_ptmem"), (_lib.ATTN_TCGEN05_V2_3PIPE, "attention2_3pipe"),
-                     (_lib.ATTN_TCGEN05_V3, "attention3"), (_lib.ATTN_TCGEN05_V4, "attention4 persistent (default)")):
+    for impl, nm in ((_lib.ATTN_TCGEN05_V3, "attention3"), (_lib.ATTN_TCGEN05_V4, "attention4 persistent (default)")):
         ms = timeit(lambda: G.attention(qkv, n_img, T, H, impl))
         res.append(dict(kernel=nm, ms=ms, tflops=4 * n_img * H * T * T * 64 / ms / 1e9))
     g, b = torch.ones(D, device=dev), torch.zeros(D, device=dev)

@@ -182,3 +182,22 @@ def test_keypoints_spair_padding_with_two_model_width(dtype):
                                           soft=soft, window=5)
         assert tuple(got.shape[-2:]) == (K, 2)
         assert (got.reshape(K, 2) - want).abs().max() < PIX_TOL, soft
+
+
+def test_pck_per_pair_with_host_side_arguments():
+    """gt / thresholds given as CPU tensors are copied inside the wrapper; with small batches those copies are the same
+    allocator size class (the regression: a freed temporary of gt was reused by the thresholds' copy before the launch)."""
+    g = torch.Generator().manual_seed(31)
+    for B in (1, 3, 4, 24):
+        K = 12
+        pred = torch.rand(B, K, 2, generator=g) * 800
+        gt = pred + torch.randn(B, K, 2, generator=g) * 30
+        vis = torch.rand(B, K, generator=g) > 0.3
+        thr = 200 + 600 * torch.rand(B, generator=g)
+        for _ in range(3):
+            got = CS.pck_per_pair(pred.cuda(), gt, vis, thr).cpu()
+            for b in range(B):
+                err = (gt[b] - pred[b]).norm(dim=-1)[vis[b]]
+                nv = max(int(vis[b].sum()), 1)
+                want = [float((err < a * thr[b]).sum()) / nv for a in (0.1, 0.05, 0.01)]
+                assert torch.allclose(got[b, :3], torch.tensor(want), atol=1e-6), (B, b)

@@ -82,8 +82,7 @@ def test_attention_fp16_operands():
     n, T, H = 2, 577, 16
     qkv = _rand((n * T, 3 * H * 64), 31, 1.0, torch.float16)
     want = _torch_attention(qkv, n, T, H)
-    for impl in (_lib.ATTN_TCGEN05, _lib.ATTN_TCGEN05_V2, _lib.ATTN_TCGEN05_V2_PTMEM, _lib.ATTN_TCGEN05_V2_3PIPE,
-                 _lib.ATTN_TCGEN05_V3, _lib.ATTN_TCGEN05_V4, _lib.ATTN_SIMT_CHECK):
+    for impl in (_lib.ATTN_TCGEN05_V3, _lib.ATTN_TCGEN05_V4, _lib.ATTN_SIMT_CHECK):
         got = G.attention(qkv, n, T, H, impl)
         assert got.dtype == torch.float16
         assert G.rel_err(got, want) < 6e-4
@@ -126,8 +125,7 @@ def _torch_attention(qkv, n, T, H):
     return (p @ v).transpose(1, 2).reshape(n * T, D)
 
 
-@pytest.mark.parametrize("impl", [_lib.ATTN_SIMT_CHECK, _lib.ATTN_TCGEN05, _lib.ATTN_TCGEN05_V2, _lib.ATTN_TCGEN05_V2_PTMEM,
-                                  _lib.ATTN_TCGEN05_V2_3PIPE, _lib.ATTN_TCGEN05_V3, _lib.ATTN_TCGEN05_V4])
+@pytest.mark.parametrize("impl", [_lib.ATTN_SIMT_CHECK, _lib.ATTN_TCGEN05_V3, _lib.ATTN_TCGEN05_V4])
 @pytest.mark.parametrize("n,T,H,scale", [(2, 577, 16, 1.0), (3, 257, 16, 2.0), (2, 196, 12, 1.0), (1, 50, 16, 1.0),
                                           (1, 128, 16, 3.0), (1, 640, 16, 1.0)])
 def test_attention(impl, n, T, H, scale):
@@ -142,11 +140,13 @@ def test_attention(impl, n, T, H, scale):
 def test_attention_tcgen05_matches_simt_check():
     n, T, H = 4, 577, 16
     qkv = _rand((n * T, 3 * H * 64), 99, 1.5)
-    a = G.attention(qkv, n, T, H, _lib.ATTN_TCGEN05)
+    a = G.attention(qkv, n, T, H, _lib.ATTN_AUTO)
     b = G.attention(qkv, n, T, H, _lib.ATTN_SIMT_CHECK)
-    c = G.attention(qkv, n, T, H, _lib.ATTN_TCGEN05_V2)
+    c = G.attention(qkv, n, T, H, _lib.ATTN_TCGEN05_V3)
     assert G.rel_err(a, b.float()) < 4e-3
     assert G.rel_err(c, b.float()) < 4e-3
+    with pytest.raises(_lib.LovrError, match="not in this build"):      # the removed generations fail loudly
+        G.attention(qkv, n, T, H, 0)
 
 
 @pytest.mark.parametrize("n,T,H", [(40, 577, 16), (70, 257, 16), (100, 196, 12), (19, 640, 16), (10, 300, 16),
