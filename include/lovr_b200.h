@@ -37,6 +37,10 @@ enum { LOVR_ATTN_SIMT_CHECK = 1,
        LOVR_ATTN_TCGEN05_V3 = 6 /* one CTA per (image, head): three softmax pipelines, P through TMEM, K/V streamed per block */,
        LOVR_ATTN_TCGEN05_V4 = 7 /* persistent: one CTA per SM, tiles of consecutive (image, head) items roll through the three pipelines */ };
 
+/* Threading: every entry point may be called from any host thread on any stream; lovr_last_error() and lovr_launch_count()
+ * are per host thread; per-kernel attributes are cached per device under a mutex (several GPUs in one process work).
+ * A lovr_tower_t owns ONE workspace: calls on the same handle must be stream-ordered (one handle per concurrent stream).
+ * The live profiler (lovr_prof_*) is a process-wide measurement aid, mutex-guarded. */
 int lovr_abi_version(void);
 const char* lovr_last_error(void);
 /* number of kernels this library has launched on the calling thread since load (bench.py's gpu_launches) */

@@ -140,12 +140,12 @@ template <int BN, int EPI, int ACT, bool F16, int RB = 2>  // RB: staging buffer
 __device__ __forceinline__ void epilogue_tile(const uint32_t t_row, const int col_tile, const int row0, const int b,
                                               const GemmArgs& p, const CUtensorMap& tmC, uint8_t* my_stage,
                                               uint64_t* my_rbar, const int lane, const uint32_t row_sw, uint32_t& g,
-                                              float& run_max) {
+                                              float& run_max, const float rs = 1.0f, const float rm = 0.0f) {
     if constexpr (EPI == EPI_BF16) {
       constexpr int CH = 64;
-      // folded LayerNorm: x = rs * acc + (rm * cw + bias); without it rs = 1, rm = 0 and the result is acc + bias exactly
-      float rs, rm;
-      ln_row_scales(p, min(row0 + lane, p.M - 1), rs, rm);
+      // folded LayerNorm: x = rs * acc + (rm * cw + bias); without it rs = 1, rm = 0 and the result is acc + bias exactly.
+      // (rs, rm come from the caller, which merges the row's statistics slots BEFORE it waits for the accumulator: the
+      // slot loads then overlap the tile's MMAs instead of sitting at the head of the epilogue)
 #pragma unroll 1
       for (int c = 0; c < BN / CH; ++c, ++g) {
         uint32_t r0[32], r1[32];
@@ -172,11 +172,15 @@ __device__ __forceinline__ void epilogue_tile(const uint32_t t_row, const int co
           }
           const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
           const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+          const float2 rs2 = make_float2(rs, rs), rm2 = make_float2(rm, rm);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
+          for (int e = 0; e < 8; e += 2) {
             const int cc = j * 8 + e;
-            const float x = fmaf(rs, __uint_as_float(cc < 32 ? r0[cc] : r1[cc - 32]), fmaf(rm, ww[e], bb[e]));
-            v[e] = apply_act<ACT>(x);
+            const float2 a2 = make_float2(__uint_as_float(cc < 32 ? r0[cc] : r1[cc - 32]),
+                                          __uint_as_float(cc < 32 ? r0[cc + 1] : r1[cc + 1 - 32]));
+            const float2 x2 = __ffma2_rn(rs2, a2, __ffma2_rn(rm2, make_float2(ww[e], ww[e + 1]), make_float2(bb[e], bb[e + 1])));
+            v[e] = apply_act<ACT>(x2.x);
+            v[e + 1] = apply_act<ACT>(x2.y);
           }
           st_shared_v4(buf_row + ((j ^ row_sw) << 4), pack16x2<F16>(v[0], v[1]), pack16x2<F16>(v[2], v[3]),
                        pack16x2<F16>(v[4], v[5]), pack16x2<F16>(v[6], v[7]));
@@ -245,7 +249,7 @@ __device__ __forceinline__ void epilogue_tile(const uint32_t t_row, const int co
           tma_load_3d(buf, &tmC, &my_rbar[gi % RB], col_tile + i * CH, row0, b);
         }
       }
-      float st_shift = 0.f, st_s1 = 0.f, st_s2 = 0.f;
+      float2 st_nshift = make_float2(0.f, 0.f), st_s1 = st_nshift, st_s2 = st_nshift;  // two lanes of partial sums
       const bool row_ok = row0 + lane < p.M;
 #pragma unroll 1
       for (int c = 0; c < NCH; ++c, ++g) {
@@ -270,26 +274,23 @@ __device__ __forceinline__ void epilogue_tile(const uint32_t t_row, const int co
           uint32_t q0, q1, q2, q3;
           const uint32_t addr = buf_row + ((j ^ row_sw) << 4);
           ld_shared_v4(addr, q0, q1, q2, q3);
-          float res[4] = {__uint_as_float(q0), __uint_as_float(q1), __uint_as_float(q2), __uint_as_float(q3)};
           float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), s0 = make_float4(1.f, 1.f, 1.f, 1.f);
           if (p.bias) b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j * 4));
           if (p.colscale) s0 = __ldg(reinterpret_cast<const float4*>(p.colscale + col0 + j * 4));
-          const float bb[4] = {b0.x, b0.y, b0.z, b0.w};
-          const float ss[4] = {s0.x, s0.y, s0.z, s0.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) res[e] += (__uint_as_float(r0[j * 4 + e]) + bb[e]) * ss[e];
-          st_shared_v4(addr, __float_as_uint(res[0]), __float_as_uint(res[1]), __float_as_uint(res[2]),
-                       __float_as_uint(res[3]));
+          // packed fp32 (FADD2 / FFMA2): two elements per instruction, the same two roundings per element as the scalar form
+          float2 ra = make_float2(__uint_as_float(q0), __uint_as_float(q1)), rb = make_float2(__uint_as_float(q2), __uint_as_float(q3));
+          ra = __ffma2_rn(__fadd2_rn(make_float2(__uint_as_float(r0[j * 4]), __uint_as_float(r0[j * 4 + 1])), make_float2(b0.x, b0.y)),
+                          make_float2(s0.x, s0.y), ra);
+          rb = __ffma2_rn(__fadd2_rn(make_float2(__uint_as_float(r0[j * 4 + 2]), __uint_as_float(r0[j * 4 + 3])), make_float2(b0.z, b0.w)),
+                          make_float2(s0.z, s0.w), rb);
+          st_shared_v4(addr, __float_as_uint(ra.x), __float_as_uint(ra.y), __float_as_uint(rb.x), __float_as_uint(rb.y));
           if (p.stats_out != nullptr) {  // (warp-uniform) statistics of the NEW residual row for the next folded LayerNorm
-            if ((c & 3) == 0 && j == 0) st_shift = res[0];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float d = res[e] - st_shift;
-              st_s1 += d;
-              st_s2 = fmaf(d, d, st_s2);
-            }
-            xh[2 * j] = pack16x2<F16>(res[0], res[1]);
-            xh[2 * j + 1] = pack16x2<F16>(res[2], res[3]);
+            if ((c & 3) == 0 && j == 0) st_nshift = make_float2(-ra.x, -ra.x);
+            const float2 da = __fadd2_rn(ra, st_nshift), db = __fadd2_rn(rb, st_nshift);
+            st_s1 = __fadd2_rn(__fadd2_rn(st_s1, da), db);
+            st_s2 = __ffma2_rn(db, db, __ffma2_rn(da, da, st_s2));
+            xh[2 * j] = pack16x2<F16>(ra.x, ra.y);
+            xh[2 * j + 1] = pack16x2<F16>(rb.x, rb.y);
           }
         }
         fence_proxy_async_smem();
@@ -305,9 +306,9 @@ __device__ __forceinline__ void epilogue_tile(const uint32_t t_row, const int co
           for (int q = 0; q < 4; ++q) dst[q] = make_uint4(xh[4 * q], xh[4 * q + 1], xh[4 * q + 2], xh[4 * q + 3]);
           if ((c & 3) == 3) {  // 128 columns done: one slot
             reinterpret_cast<float4*>(p.stats_out)[static_cast<size_t>(row0 + lane) * (p.N / kLnPartCols) + col0 / kLnPartCols] =
-                make_float4(st_shift, st_s1, st_s2, 0.f);
-            st_s1 = 0.f;
-            st_s2 = 0.f;
+                make_float4(-st_nshift.x, st_s1.x + st_s1.y, st_s2.x + st_s2.y, 0.f);
+            st_s1 = make_float2(0.f, 0.f);
+            st_s2 = st_s1;
           }
         }
       }
@@ -467,11 +468,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int ni = 0; ni < p.n_inner; ++ni) {
         const int nt = ng * p.n_inner + ni;
         const int col_tile = nt * BN;
+        float rs = 1.0f, rm = 0.0f;
+        if constexpr (EPI == EPI_BF16) ln_row_scales(p, min(row0 + lane, p.M - 1), rs, rm);
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
 
-        epilogue_tile<BN, EPI, ACT, F16>(t_row, col_tile, row0, b, p, tmC, my_stage, my_rbar, lane, row_sw, g, run_max);
+        epilogue_tile<BN, EPI, ACT, F16>(t_row, col_tile, row0, b, p, tmC, my_stage, my_rbar, lane, row_sw, g, run_max, rs, rm);
         // all TMEM reads of this accumulator are complete (tcgen05.wait::ld above)
         tc_fence_before();
         __syncwarp();

@@ -213,11 +213,13 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const int nt = unit % n_tiles;
       const int mt = unit / n_tiles;
       const int row0 = mt * 256 + static_cast<int>(rank) * 128 + quarter * 32;
+      float rs = 1.0f, rm = 0.0f;  // folded LayerNorm: the row's statistics are merged while the tile's MMAs still run
+      if constexpr (EPI == EPI_BF16) ln_row_scales(p, min(row0 + lane, p.M - 1), rs, rm);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
       epilogue_tile<CW, EPI, ACT, F16, RB>(t_row + chalf * CW, nt * BN + chalf * CW, row0, 0, p, tmC, my_stage, my_rbar, lane,
-                                          row_sw, g, run_max);
+                                          row_sw, g, run_max, rs, rm);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[acc]), 0));  // leader's barrier
