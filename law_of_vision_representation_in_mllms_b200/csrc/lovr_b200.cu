@@ -24,6 +24,7 @@
 #include "gemm.cuh"
 #include "gemm2.cuh"
 #include "gram.cuh"
+#include "kpsim.cuh"
 #include "preprocess.cuh"
 #include "rowwise.cuh"
 #include "scores.cuh"
@@ -1170,6 +1171,27 @@ int lovr_c_score_keypoints(const void* desc1, const void* desc2, int32_t dtype, 
   if (n_pairs > 65535) return fail(LOVR_E_ARG, "c_score_keypoints: at most 65535 pairs per call");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   float* rows = static_cast<float*>(workspace);
+  // bf16 descriptors: the keypoint rows as a skinny tcgen05 GEMM (kpsim.cuh) — the SM only keeps TMA loads of the target
+  // descriptors in flight.  Needs more k-blocks than pipeline stages and the source rows resident in shared memory.
+  static const int kp_tc_env = [] { const char* e = getenv("LOVR_KP_TENSOR"); return e ? atoi(e) : 1; }();
+  if (kp_tc_env && dtype == LOVR_DT_BF16 && D % 64 == 0 && D / 64 > kKpStages && kp_smem_bytes(D) <= 227 * 1024) {
+    CUtensorMap ta;
+    if (int rc = make_tmap(&ta, desc2, 2, D, PP, n_pairs, D, static_cast<uint64_t>(D) * PP, 64, kBM)) return rc;
+    const size_t smem = kp_smem_bytes(D);
+    if (int rc = ensure_smem(reinterpret_cast<const void*>(kpsim_tcgen05_kernel), smem)) return rc;
+    KpArgs a{};
+    a.PP = PP; a.D = D; a.K = K; a.n_pairs = static_cast<int>(n_pairs);
+    a.d1 = static_cast<const uint16_t*>(desc1); a.idx = patch_idx; a.out = rows;
+    const int m_tiles = (PP + kBM - 1) / kBM;
+    const long long units = static_cast<long long>(n_pairs) * ((m_tiles + kKpTilesPerUnit - 1) / kKpTilesPerUnit);
+    const int grid = units < device_info().sms ? static_cast<int>(units) : device_info().sms;
+    {
+      ProfScope prof_scope(s, LOVR_PROF_OTHER, static_cast<double>(n_pairs) * (PP + K) * D * 2.0);  // bytes: HBM-bound
+      kpsim_tcgen05_kernel<<<grid, kKpThreads, smem, s>>>(ta, a);
+    }
+    LAUNCH_CHECK("kpsim_tcgen05_kernel");
+    return launch_flow_rows(rows, PP, static_cast<size_t>(n_pairs) * K, P, window, soft, anno_size / P, kps_out, nullptr, s);
+  }
   // The K normalised source rows live in shared memory (K * D floats).  SPair-71k pads to 30 keypoints and the two-model
   // concat has D = 2048: 240 KB, above the 227 KB a block may opt in to — so K is split into equal chunks that fit.
   constexpr size_t kKpSmemBudget = 200 * 1024;

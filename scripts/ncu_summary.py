@@ -16,7 +16,6 @@ WANT = {
     "gpu__time_duration.sum": "ms",
     "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active": "tensor %",
     "sm__throughput.avg.pct_of_peak_sustained_elapsed": "SM %",
-    "dram__throughput.avg.pct_of_peak_sustained_elapsed": "DRAM %",
     "dram__bytes_read.sum": "DRAM read MB",
     "dram__bytes_write.sum": "DRAM write MB",
     "lts__t_sector_hit_rate.pct": "L2 hit %",
@@ -58,7 +57,7 @@ def rows_of(rep):
 
 
 def short(name):
-    n = name.split("(")[0].replace("lovr::", "")
+    n = name.split("(")[0].replace("lovr::", "").replace("void ", "")
     return n if len(n) < 70 else n[:67] + "..."
 
 

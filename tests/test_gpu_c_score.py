@@ -201,3 +201,22 @@ def test_pck_per_pair_with_host_side_arguments():
                 nv = max(int(vis[b].sum()), 1)
                 want = [float((err < a * thr[b]).sum()) / nv for a in (0.1, 0.05, 0.01)]
                 assert torch.allclose(got[b, :3], torch.tensor(want), atol=1e-6), (B, b)
+
+
+@pytest.mark.parametrize("n,P,K,D", [(3, 60, 12, 1024), (40, 24, 30, 1024), (200, 11, 5, 768), (2, 16, 1, 1792), (5, 37, 32, 512)])
+def test_keypoints_bf16_tensor_core_path(n, P, K, D):
+    """bf16 descriptors with D >= 448 take the tcgen05 keypoint kernel (kpsim.cuh): ragged last tiles, one-tile units
+    (P = 11), more units than SMs (persistent loop, source rows re-gathered per unit), K = 1 ... 32."""
+    g = torch.Generator().manual_seed(n * 100 + P)
+    d1 = (torch.randn(n, P * P, D, generator=g) * (0.3 + torch.rand(n, P * P, 1, generator=g))).bfloat16()
+    d2 = (0.5 * torch.roll(d1.float(), 5, dims=1) + 0.6 * torch.randn(n, P * P, D, generator=g)).bfloat16()
+    idx = torch.randint(0, P * P, (n, K), generator=g).numpy()
+    for soft in (True, False):
+        got = CS.keypoint_transformation(d1.cuda(), d2.cuda(), idx, soft=soft, window=5).cpu()
+        assert tuple(got.shape) == (n, K, 2)
+        for b in sorted({0, n // 2, n - 1}):
+            want = co.keypoint_transformation(co.normalize_feats(d1[b:b + 1].float()), co.normalize_feats(d2[b:b + 1].float()),
+                                              idx[b], P, soft=soft, window=5)
+            assert (got[b] - want).abs().max() < PIX_TOL, (b, soft, (got[b] - want).abs().max())
+    again = CS.keypoint_transformation(d1.cuda(), d2.cuda(), idx, soft=True, window=5).cpu()
+    assert torch.equal(again, CS.keypoint_transformation(d1.cuda(), d2.cuda(), idx, soft=True, window=5).cpu())
