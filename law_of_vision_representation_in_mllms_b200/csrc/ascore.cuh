@@ -36,12 +36,12 @@ struct AScoreArgs {
   float* rowmax;         // [n_pairs, x]
 };
 
-template <int BN>
+template <int BN, int STAGES = 4>
 struct AScoreSmem {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = 4;   // (five 40 KB stages and an L2 prefetch 8 steps ahead were measured slower: 10.8 vs 9.4 ms at C3)
+  static constexpr int kStages = STAGES;
   static constexpr int kTotal = kStages * kStageBytes + 2 * kBM * 4 /*inv_other*/ + 256 /*barriers*/ + 1024 /*align*/;
 };
 
@@ -64,10 +64,10 @@ __device__ __forceinline__ float row_sumsq_128B(uint32_t row_addr, int t) {
   return s0 + s1;
 }
 
-template <int BN>
+template <int BN, int STAGES = 4>
 __global__ void __launch_bounds__(kAsThreads, 1)
 ascore_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const AScoreArgs p) {
-  using L = AScoreSmem<BN>;
+  using L = AScoreSmem<BN, STAGES>;
   constexpr uint32_t kTmemCols = (2 * BN <= 256) ? 256 : 512;
   constexpr uint32_t kIdesc = make_idesc_16(kBM, BN, 0, 0, false);
   constexpr int kAsStages = L::kStages;

@@ -937,6 +937,11 @@ int lovr_a_score_maxcos(const void* other, const void* ref, int32_t dtype, int64
     LAUNCH_CHECK("rownorm_inv_bf16_kernel");
     size_t smem = 0;
     const void* kern = nullptr;
+    static const int stages5 = [] { const char* e = getenv("LOVR_A_STAGES"); return e ? atoi(e) == 5 : 0; }();
+    if (bn == 192 && stages5) {  // measurement switch: five 40 KB stages
+      smem = AScoreSmem<192, 5>::kTotal;
+      kern = reinterpret_cast<const void*>(ascore_tcgen05_kernel<192, 5>);
+    } else
     if (bn == 128) { smem = AScoreSmem<128>::kTotal; kern = reinterpret_cast<const void*>(ascore_tcgen05_kernel<128>); }
     else if (bn == 192) { smem = AScoreSmem<192>::kTotal; kern = reinterpret_cast<const void*>(ascore_tcgen05_kernel<192>); }
     else { smem = AScoreSmem<256>::kTotal; kern = reinterpret_cast<const void*>(ascore_tcgen05_kernel<256>); }
@@ -952,7 +957,8 @@ int lovr_a_score_maxcos(const void* other, const void* ref, int32_t dtype, int64
     const int grid = units < device_info().sms ? static_cast<int>(units) : device_info().sms;
     {
       ProfScope prof_scope(s, LOVR_PROF_OTHER, 2.0 * x * static_cast<double>(y) * D * n_pairs);
-      if (bn == 128) ascore_tcgen05_kernel<128><<<grid, kAsThreads, smem, s>>>(ta, tb, a);
+      if (bn == 192 && stages5) ascore_tcgen05_kernel<192, 5><<<grid, kAsThreads, smem, s>>>(ta, tb, a);
+      else if (bn == 128) ascore_tcgen05_kernel<128><<<grid, kAsThreads, smem, s>>>(ta, tb, a);
       else if (bn == 192) ascore_tcgen05_kernel<192><<<grid, kAsThreads, smem, s>>>(ta, tb, a);
       else ascore_tcgen05_kernel<256><<<grid, kAsThreads, smem, s>>>(ta, tb, a);
     }
