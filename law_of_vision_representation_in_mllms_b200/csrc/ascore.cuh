@@ -18,7 +18,7 @@
 // Barriers: full[s] (TMA -> MMA + norm), empty[s] (count 1 + 4: tcgen05.commit + one arrive per norm warp),
 // tmem_full/tmem_empty[acc] as in gemm.cuh, aux_full[acc] (count 4): the norm warps are done with tile (mt, nt) — they
 // arrive once per tile, so its phase follows the accumulator's; the row scales of a unit are published with its first tile,
-// in a slot that alternates with the unit's parity.  Needs K/64 > stages (4) (the phase argument: the norm warps cannot run a
+// in a slot that alternates with the unit's parity.  Needs K/64 > stages (4, or 5 for BN = 192) (the phase argument: the norm warps cannot run a
 // whole tile ahead of the MMA issuer).
 #pragma once
 #include "gemm.cuh"

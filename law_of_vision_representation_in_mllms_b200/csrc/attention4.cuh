@@ -17,7 +17,8 @@
 // Register split (setmaxnreg): 80 for the four control warps, 144 for the twelve softmax warps.  Measured per 64 images
 // at T = 577 with control budgets 40 / 56 / 80 / 104 / 128 (no rebalancing): 0.240 / 0.217 / 0.209 / 0.240 / 0.314 ms — at 40
 // registers the MMA issue loop spills to local memory, and the issuer's loop time is on the critical path.
-// Tried and dropped (measured slower): moving every 4th / 2nd exponential to the FMA pipe (cubic 2^f, +5 % / +15 %: the
+// Tried and dropped (measured slower): letting a softmax warp whose 32 rows all lie past T (fourth warp of the last tile at
+// T = 577) skip its loads / exponentials / P store (0.195 -> 0.203 ms per 64 images); moving every 4th / 2nd exponential to the FMA pipe (cubic 2^f, +5 % / +15 %: the
 // kernel is issue- and latency-bound, not MUFU-bound); ex2.approx.f16x2 (compiles to two MUFU.EX2.F16); 32-column half units.
 #pragma once
 #include "attention3.cuh"

@@ -45,6 +45,8 @@ class FeatureExtractor:
         self._copy_in = torch.cuda.Stream(self.device)
         self._copy_out = torch.cuda.Stream(self.device)
         self._bufs = None
+        self._raw_host = [None, None]      # pinned staging for packed raw images (run_images), reused across calls
+        self._raw_done = [None, None]      # event after the H2D copy that last read the staging buffer
 
     def _alloc(self, pixel_shapes, pixel_dtype, out_shape, out_dtype):
         key = (tuple(pixel_shapes), pixel_dtype, tuple(out_shape), out_dtype)
@@ -145,10 +147,17 @@ class FeatureExtractor:
             b["out_free"][k].record(main)
         for i, s in enumerate(range(0, n, c)):
             e, k = min(n, s + c), i & 1
-            host_raw, offsets, hw = PP.pack_images(images[s:e])
+            if self._raw_done[k] is not None:
+                self._raw_done[k].synchronize()          # the copy that last read this staging buffer has finished
+            def grow(nbytes, k=k):
+                self._raw_host[k] = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, pin_memory=True)
+                return self._raw_host[k]
+            host_raw, offsets, hw = PP.pack_images(images[s:e], self._raw_host[k], grow)
             with torch.cuda.stream(self._copy_in):
                 dev_raw = host_raw.to(self.device, non_blocking=True)
                 b["in_ready"][k].record(self._copy_in)
+                self._raw_done[k] = torch.cuda.Event()
+                self._raw_done[k].record(self._copy_in)
             dev_raw.record_stream(main)
             main.wait_event(b["in_ready"][k])
             main.wait_event(b["out_free"][k])
@@ -236,9 +245,13 @@ def extract_folder(extractor, input_dir, output_dir, layout="c_score", model_tag
             cfg.mean[i], cfg.std[i] = 0.0, 1.0
         pre_cfgs, pixel_dtype = [cfg], torch.float32
     launches0 = _lib.launch_count() if todo else 0
+    host_buf = None      # one pinned output buffer for the whole job (every file below is a clone of its rows)
     for s0 in range(0, len(todo), batch):
         part = todo[s0:s0 + batch]
-        feats = extractor.run_images([loader(p) for _, _, p in part], pixel_dtype=pixel_dtype, pre_cfgs=pre_cfgs)
+        kw = {} if host_buf is None else dict(host_out=host_buf[: len(part)])
+        feats = extractor.run_images([loader(p) for _, _, p in part], pixel_dtype=pixel_dtype, pre_cfgs=pre_cfgs, **kw)
+        if host_buf is None and len(part) == batch:
+            host_buf = feats
         g = int(round(feats.shape[1] ** 0.5))
         for (cls, stem, src), f in zip(part, feats):
             path = out_path(cls, stem, src)

@@ -25,7 +25,7 @@ class _StubExtractor:
         self.towers = [_StubTower()]
         self.calls = []
 
-    def run_images(self, images, pixel_dtype=torch.bfloat16, pre_cfgs=None, **kw):
+    def run_images(self, images, pixel_dtype=torch.bfloat16, pre_cfgs=None, host_out=None, **kw):
         self.calls.append((len(images), pixel_dtype, None if pre_cfgs is None else int(pre_cfgs[0].crop_size)))
         out = torch.zeros(len(images), 4, 8, dtype=pixel_dtype)
         for i, im in enumerate(images):
