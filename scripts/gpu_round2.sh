@@ -12,6 +12,10 @@ echo "=== ncu full (step kernels)"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'gemm2?_tcgen05|attention4_tcgen05|layernorm' -s 40 -c 12 -f -o gpurun_out/r02_step \
   python bench.py --steps 1 --warmup 1 --batch 128 --chunk 128 --no-cpu-baseline --no-scores > gpurun_out/ncu_full.log 2>&1
 echo "=== ncu full (score kernels)"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'gram_tcgen05|ascore_tcgen05|rownorm_inv|kp_sim_rows|flow_rows|gemm_tcgen05' -s 6 -c 10 -f -o gpurun_out/r02_scores \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'gram_tcgen05|ascore_tcgen05|kpsim_tcgen05|rownorm_inv|kp_sim_rows|flow_rows|gemm_tcgen05' -c 30 -f -o gpurun_out/r02_scores \
   python scripts/score_kernels_once.py > gpurun_out/ncu_scores.log 2>&1
+# the reports are too large to travel back (64 MiB limit): summarise them here, keep the tables and the traffic figure only
+python scripts/ncu_summary.py gpurun_out/r02_step.ncu-rep gpurun_out/r02_scores.ncu-rep > gpurun_out/r02_ncu_summary.md 2> gpurun_out/ncu_summary.err
+cp profiles/r02_traffic.json gpurun_out/r02_traffic.json 2>/dev/null
+rm -f gpurun_out/r02_step.ncu-rep gpurun_out/r02_scores.ncu-rep
 ls -la gpurun_out | tail -12

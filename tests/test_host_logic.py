@@ -73,3 +73,14 @@ def test_pil_inputs_are_converted_to_rgb_like_do_convert_rgb():
     g = host.numpy()[: 6 * 8 * 3].reshape(6, 8, 3)
     assert np.array_equal(g, np.asarray(gray.convert("RGB")))
     assert np.array_equal(host.numpy()[6 * 8 * 3:].reshape(4, 5, 3), np.asarray(rgba.convert("RGB")))
+
+
+def test_extractor_chunk_schedule_covers_every_image_once():
+    from law_of_vision_representation_in_mllms_b200.extract import chunk_schedule
+    for n in (1, 2, 3, 5, 100, 128, 129, 255, 256, 257, 300, 511, 512, 513, 1000, 10000):
+        for c in (1, 4, 64, 128, 256):
+            ch = chunk_schedule(n, c)
+            assert ch[0][0] == 0 and ch[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(ch, ch[1:]))
+            assert all(0 < hi - lo <= c for lo, hi in ch)
+    assert [hi - lo for lo, hi in chunk_schedule(512, 256)] == [128, 256, 128]
