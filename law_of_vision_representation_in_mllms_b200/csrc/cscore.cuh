@@ -18,12 +18,8 @@ constexpr int kMaxKps = 32;    // keypoints per pair (SPair-71k: <= 30)
 //                   window == 0: plain soft-argmax over the whole row.
 // flow[r] = ((E[x]+1)(P-1)/2, (E[y]+1)(P-1)/2) in patch units (:239-255, :264-265), x,y on linspace(-1,1,P).
 // If stride > 0 the row is a keypoint row and out = clamp(flow,0,P-1)*stride + floor(stride/2)   (:369,:376-377).
-// part_max / part_arg (optional, dense path): per row `nparts` partial (maximum, first index) pairs left by the similarity
-// GEMM's epilogue, one per n tile in column order — merged here, so the row is only read inside the window.
 __global__ void flow_rows_kernel(const float* __restrict__ sim, size_t ld, size_t rows, int P, int window, float beta,
-                                 int mode, float stride, float* __restrict__ flow, int* __restrict__ argmax_out,
-                                 const float* __restrict__ part_max = nullptr, const int* __restrict__ part_arg = nullptr,
-                                 int nparts = 0) {
+                                 int mode, float stride, float* __restrict__ flow, int* __restrict__ argmax_out) {
   __shared__ float lin[kMaxGrid];
   if (threadIdx.x < P) lin[threadIdx.x] = static_cast<float>(-1.0 + threadIdx.x * (2.0 / (P - 1)));
   __syncthreads();
@@ -35,16 +31,9 @@ __global__ void flow_rows_kernel(const float* __restrict__ sim, size_t ld, size_
   // ---- row argmax, first index on ties (torch.argmax)
   float bv = -INFINITY;
   int bi = 0x7fffffff;
-  if (part_arg != nullptr) {
-    for (int q = lane; q < nparts; q += 32) {  // partials are in column order: strict > keeps the first index
-      const float v = __ldg(part_max + row * nparts + q);
-      if (v > bv) { bv = v; bi = __ldg(part_arg + row * nparts + q); }
-    }
-  } else {
-    for (int t = lane; t < PP; t += 32) {
-      const float v = __ldg(s + t);
-      if (v > bv) { bv = v; bi = t; }
-    }
+  for (int t = lane; t < PP; t += 32) {
+    const float v = __ldg(s + t);
+    if (v > bv) { bv = v; bi = t; }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {

@@ -57,11 +57,6 @@ struct GemmArgs {
   float* stats_out;       // [M][N / 128][4] or nullptr
   void* xhat_out;         // 16-bit [M, N], row stride ld_xhat elements, or nullptr
   long long ld_xhat;
-  // EPI_F32: also the row maximum and its first index over the columns < n_valid of each unit's n tiles (the values
-  // compared are the ones stored): [batch, M, n_groups] partials — the dense C-score flow merges them instead of re-reading
-  // whole similarity rows to find the argmax
-  float* part_max;        // or nullptr
-  int* part_arg;
 };
 
 // Row statistics travel as one slot per 128 columns: (shift, sum(x - shift), sum((x - shift)^2), unused) with shift = the
@@ -145,8 +140,7 @@ template <int BN, int EPI, int ACT, bool F16, int RB = 2>  // RB: staging buffer
 __device__ __forceinline__ void epilogue_tile(const uint32_t t_row, const int col_tile, const int row0, const int b,
                                               const GemmArgs& p, const CUtensorMap& tmC, uint8_t* my_stage,
                                               uint64_t* my_rbar, const int lane, const uint32_t row_sw, uint32_t& g,
-                                              float& run_max, const float rs = 1.0f, const float rm = 0.0f,
-                                              int* run_arg = nullptr) {
+                                              float& run_max, const float rs = 1.0f, const float rm = 0.0f) {
     if constexpr (EPI == EPI_BF16) {
       constexpr int CH = 64;
       // folded LayerNorm: x = rs * acc + (rm * cw + bias); without it rs = 1, rm = 0 and the result is acc + bias exactly.
@@ -226,16 +220,6 @@ __device__ __forceinline__ void epilogue_tile(const uint32_t t_row, const int co
             v[1] *= s0.y * rs;
             v[2] *= s0.z * rs;
             v[3] *= s0.w * rs;
-          }
-          if (run_arg != nullptr) {  // (warp-uniform) running argmax of exactly the values that are stored
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int col = col0 + j * 4 + e;
-              if (col < p.n_valid && v[e] > run_max) {
-                run_max = v[e];
-                *run_arg = col;
-              }
-            }
           }
           st_shared_v4(buf_row + ((j ^ row_sw) << 4), __float_as_uint(v[0]), __float_as_uint(v[1]),
                        __float_as_uint(v[2]), __float_as_uint(v[3]));
@@ -481,7 +465,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int b = unit / (n_groups * m_tiles);
       const int row0 = mt * kBM + quarter * 32;
       float run_max = -INFINITY;
-      int run_arg = 0;
       for (int ni = 0; ni < p.n_inner; ++ni) {
         const int nt = ng * p.n_inner + ni;
         const int col_tile = nt * BN;
@@ -491,8 +474,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tc_fence_after();
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
 
-        epilogue_tile<BN, EPI, ACT, F16>(t_row, col_tile, row0, b, p, tmC, my_stage, my_rbar, lane, row_sw, g, run_max, rs, rm,
-                                         (EPI == EPI_F32 && p.part_arg != nullptr) ? &run_arg : nullptr);
+        epilogue_tile<BN, EPI, ACT, F16>(t_row, col_tile, row0, b, p, tmC, my_stage, my_rbar, lane, row_sw, g, run_max, rs, rm);
         // all TMEM reads of this accumulator are complete (tcgen05.wait::ld above)
         tc_fence_before();
         __syncwarp();
@@ -505,13 +487,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (row < p.M) {
           const size_t idx = static_cast<size_t>(b) * p.M + row;
           p.rowmax[idx] = run_max * __ldg(p.rowscale + idx);
-        }
-      }
-      if constexpr (EPI == EPI_F32) {
-        if (p.part_arg != nullptr && row0 + lane < p.M) {
-          const size_t idx = (static_cast<size_t>(b) * p.M + row0 + lane) * n_groups + ng;
-          p.part_max[idx] = run_max;
-          p.part_arg[idx] = run_arg;
         }
       }
     }

@@ -997,7 +997,7 @@ int lovr_a_score_maxcos(const void* other, const void* ref, int32_t dtype, int64
 // ====================================================================================== C score
 namespace {
 struct CScoreLayout {
-  size_t inv1, inv2, sim, arg, split1, split2, total;
+  size_t inv1, inv2, sim, split1, split2, total;
   int scale_ld, sim_ld;
 };
 CScoreLayout c_layout(int dtype, int64_t n, int P, int D) {
@@ -1009,7 +1009,6 @@ CScoreLayout c_layout(int dtype, int64_t n, int P, int D) {
   l.inv1 = off; off += align_up(static_cast<size_t>(n) * l.scale_ld * 4, 1024);
   l.inv2 = off; off += align_up(static_cast<size_t>(n) * l.scale_ld * 4, 1024);
   l.sim = off; off += align_up(static_cast<size_t>(n) * PP * l.sim_ld * 4, 1024);
-  l.arg = off; off += 2 * align_up(static_cast<size_t>(n) * PP * ((PP + 255) / 256) * 4, 1024);   // per-n-tile row (max, argmax) partials from the GEMM epilogue
   if (dtype == LOVR_DT_F32) {
     l.split1 = off; off += align_up(static_cast<size_t>(n) * PP * 3 * D * 2, 1024);
     l.split2 = off; off += align_up(static_cast<size_t>(n) * PP * 3 * D * 2, 1024);
@@ -1025,11 +1024,10 @@ int check_c_args(const void* d1, const void* d2, int dtype, int64_t n, int P, in
   return 0;
 }
 int launch_flow_rows(const float* sim, size_t ld, size_t rows, int P, int window, int soft, float stride, float* flow,
-                     int* argmax, cudaStream_t s, const float* part_max = nullptr, const int* part_arg = nullptr,
-                     int nparts = 0) {
+                     int* argmax, cudaStream_t s) {
   const int wpb = 8;
   lovr::flow_rows_kernel<<<static_cast<unsigned>((rows + wpb - 1) / wpb), wpb * 32, 0, s>>>(
-      sim, ld, rows, P, window, 0.02f, soft ? 1 : 0, stride, flow, argmax, part_max, part_arg, nparts);
+      sim, ld, rows, P, window, 0.02f, soft ? 1 : 0, stride, flow, argmax);
   LAUNCH_CHECK("flow_rows_kernel");
   return 0;
 }
@@ -1044,7 +1042,7 @@ namespace {
 // n(desc1) n(desc2)^T for every pair into the workspace (layout l): inverse norms, optional fp32 -> 3 x bf16 split,
 // batched tcgen05 GEMM with row/column scales.  Shared by the dense flow and the mutual-NN distance.
 int c_dense_similarity(const void* desc1, const void* desc2, int32_t dtype, int64_t n_pairs, int32_t P, int32_t D,
-                       uint8_t* base, const CScoreLayout& l, cudaStream_t s, bool partial_argmax = false) {
+                       uint8_t* base, const CScoreLayout& l, cudaStream_t s) {
   using namespace lovr;
   float* inv1 = reinterpret_cast<float*>(base + l.inv1);
   float* inv2 = reinterpret_cast<float*>(base + l.inv2);
@@ -1083,11 +1081,6 @@ int c_dense_similarity(const void* desc1, const void* desc2, int32_t dtype, int6
   GemmArgs g{};
   g.M = PP; g.N = PP; g.K = K; g.batch = static_cast<int>(n_pairs); g.n_inner = 1;
   g.bias = nullptr; g.colscale = inv2; g.rowscale = inv1; g.rowmax = nullptr; g.n_valid = PP; g.scale_ld = l.scale_ld;
-  if (partial_argmax) {  // per (row, n tile): the maximum of the stored values and its first index
-    const size_t half = align_up(static_cast<size_t>(n_pairs) * PP * ((PP + 255) / 256) * 4, 1024);
-    g.part_max = reinterpret_cast<float*>(base + l.arg);
-    g.part_arg = reinterpret_cast<int*>(base + l.arg + half);
-  }
   return launch_gemm(256, EPI_F32, ACT_NONE, false, ta, tb, tc, g, s);
 }
 struct MnnLayout {
@@ -1118,15 +1111,9 @@ int lovr_c_score_flow(const void* desc1, const void* desc2, int32_t dtype, int64
   if (reinterpret_cast<uintptr_t>(workspace) & 1023) return fail(LOVR_E_ARG, "workspace must be 1024-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   auto base = static_cast<uint8_t*>(workspace);
-  // the row maxima come out of the similarity GEMM's epilogue per n tile (the values it compares are the ones it stores), so
-  // the flow kernel merges 15 partials per row and reads the row only inside its window: 0.8 KB instead of 14 KB at P = 60
-  static const int fuse_env = [] { const char* e = getenv("LOVR_C_ARGMAX_FUSED"); return e ? atoi(e) : 1; }();
-  if (int rc = c_dense_similarity(desc1, desc2, dtype, n_pairs, P, D, base, l, s, fuse_env != 0)) return rc;
-  const int nparts = (P * P + 255) / 256;
-  const size_t half = align_up(static_cast<size_t>(n_pairs) * P * P * nparts * 4, 1024);
+  if (int rc = c_dense_similarity(desc1, desc2, dtype, n_pairs, P, D, base, l, s)) return rc;
   return launch_flow_rows(reinterpret_cast<float*>(base + l.sim), l.sim_ld, static_cast<size_t>(n_pairs) * P * P, P,
-                          window, soft, 0.f, flow, argmax, s, fuse_env ? reinterpret_cast<float*>(base + l.arg) : nullptr,
-                          fuse_env ? reinterpret_cast<int*>(base + l.arg + half) : nullptr, fuse_env ? nparts : 0);
+                          window, soft, 0.f, flow, argmax, s);
 }
 
 size_t lovr_c_score_mutual_nn_workspace_bytes(int32_t dtype, int64_t n_pairs, int32_t P, int32_t D) {
