@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblovr_b200.so")
+# LOVR_B200_LIB: load an experiment build of the same ABI instead (build.py --out ...); never a different implementation
+LIB_PATH = os.environ.get("LOVR_B200_LIB") or os.path.join(_HERE, "liblovr_b200.so")
 
 OK, E_ARG, E_CUDA, E_UNSUPPORTED, E_NOMEM = 0, -1, -2, -3, -4
 DT_F32, DT_BF16, DT_F16 = 0, 1, 2

@@ -1,6 +1,9 @@
 """Build liblovr_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
 
-    python -m law_of_vision_representation_in_mllms_b200.build [--force] [--verbose]
+    python -m law_of_vision_representation_in_mllms_b200.build [--force] [--verbose] [--out PATH -DNAME=1 ...]
+
+`--out` / `-D...` build an experiment variant next to the product library (A/B timing of a compile-time switch; load it
+with LOVR_B200_LIB=PATH).  The product library is always liblovr_b200.so with no extra defines.
 """
 import os
 import subprocess
@@ -22,19 +25,21 @@ def _newest_source_mtime():
     return m
 
 
-def build(force=False, verbose=False):
-    if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= _newest_source_mtime():
-        return OUT
+def build(force=False, verbose=False, out=OUT, defines=()):
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= _newest_source_mtime():
+        return out
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
-    cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + list(defines) + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed building liblovr_b200.so")
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    _out = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else OUT
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, out=_out,
+                defines=[a for a in sys.argv[1:] if a.startswith("-D")]))

@@ -88,7 +88,7 @@ ascore_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   uint64_t* aux_full = tmem_empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_full + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_index(), lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -110,7 +110,7 @@ ascore_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = warp_uniform(*tmem_slot);
 
   if (warp == 0) {
     if (lane == 0) {

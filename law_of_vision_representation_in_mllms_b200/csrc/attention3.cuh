@@ -115,7 +115,7 @@ attention3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
   uint64_t* v_full = bars + kAttnMaxBlocks;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kPipeBar + 8 * NP);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_index(), lane = threadIdx.x & 31;
   const int n = blockIdx.x / H, h = blockIdx.x % H;
   const int D = H * 64;
   const int q_tiles = (T + 127) / 128;
@@ -143,7 +143,7 @@ attention3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = warp_uniform(*tmem_slot);
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(80));  // 40 spills the MMA issue loop: see attention4.cuh

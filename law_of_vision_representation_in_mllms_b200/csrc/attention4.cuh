@@ -62,7 +62,10 @@ attention4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
   uint64_t* v_full1 = bars + kSet1 + kAttnMaxBlocks;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kSet1 + 2 * kAttnMaxBlocks);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: the compiler then KNOWS it is warp-uniform and keeps everything derived from it (pipeline
+  // index, TMEM / shared-memory addresses, descriptors) on the uniform datapath — tcgen05.mma takes uniform-register operands,
+  // and values it cannot prove uniform go through an ELECT / R2UR loop per instruction (~150 cycles per MMA, measured)
+  const int warp = uniform_warp_index(), lane = threadIdx.x & 31;
   const int D = H * 64;
   const int q_tiles = (T + 127) / 128;
   // this CTA's items: blockIdx.x, blockIdx.x + gridDim.x, ...; its tiles in one rolling sequence, tile s -> pipeline s % 3
@@ -102,7 +105,7 @@ attention4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnA
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = warp_uniform(*tmem_slot);
 
   if (warp < 4) {
     if constexpr (RC < 128) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(RC));

@@ -355,7 +355,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* resid_bar = bars + 2 * kStages + 4;   // [kEpiWarps][2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4 + 2 * kEpiWarps);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_index();
   const int lane = threadIdx.x & 31;
 
   const int m_tiles = (p.M + kBM - 1) / kBM;
@@ -386,7 +386,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = warp_uniform(*tmem_slot);
 
   if (warp == 0) {
     // ===================================================================== TMA producer

@@ -107,7 +107,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint64_t* resid_bar = bars + 2 * kStages2 + 4;   // [kEpiWarps][RB]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages2 + 4 + RB * EW);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_index();
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1;
@@ -141,7 +141,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = warp_uniform(*tmem_slot);
 
   if (warp == 0) {
     // ===================================================================== TMA producer (both CTAs)

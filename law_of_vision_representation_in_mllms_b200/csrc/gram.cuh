@@ -83,7 +83,7 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmXa, const __grid_const
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_index(), lane = threadIdx.x & 31;
   const int Dz = p.Dx + p.Dy;
   const int units = p.n_tiles * p.n_ranges;
   constexpr int kKb = kGramChunk / 64;  // k-blocks per accumulation run
@@ -110,7 +110,7 @@ gram_tcgen05_kernel(const __grid_constant__ CUtensorMap tmXa, const __grid_const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = warp_uniform(*tmem_slot);
 
   // chunk range of unit u
   auto unit_chunks = [&](int u, int* c0, int* c1, int* i, int* j) {

@@ -68,7 +68,7 @@ kpsim_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const KpArgs p) {
   uint64_t* b_free = b_ready + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_free + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_index(), lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     for (int i = 0; i < kKpStages; ++i) {
@@ -91,7 +91,7 @@ kpsim_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const KpArgs p) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = warp_uniform(*tmem_slot);
 
   auto unit_tiles = [&](int u, int* b, int* t0, int* t1) {
     *b = u / groups;

@@ -21,6 +21,26 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 
+// Warp-uniform values THE COMPILER CAN PROVE uniform.  tcgen05.mma / tcgen05.commit / TMA take their descriptors, TMEM and
+// shared-memory addresses from uniform registers; a value derived from threadIdx.x >> 5 or loaded from shared memory is
+// uniform in fact but not provably, and ptxas then wraps every such instruction in an ELECT + R2UR.BROADCAST loop (seen in
+// the SASS of the attention kernel: 7 broadcasts per UTCHMMA).  A shuffle from lane 0 is uniform by construction, so
+// everything derived from it stays on the uniform datapath.  -DLOVR_NO_UNIFORM_HINT=1 restores the plain forms (A/B timing).
+__device__ __forceinline__ int uniform_warp_index() {
+#if defined(LOVR_NO_UNIFORM_HINT)
+  return static_cast<int>(threadIdx.x >> 5);
+#else
+  return __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+#endif
+}
+__device__ __forceinline__ uint32_t warp_uniform(uint32_t v) {
+#if defined(LOVR_NO_UNIFORM_HINT)
+  return v;
+#else
+  return __shfl_sync(0xffffffffu, v, 0);
+#endif
+}
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
