@@ -45,8 +45,18 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Arrive on an mbarrier of the PEER CTA (cluster address).  Default semantics (release at CTA scope), the form CUTLASS uses
+// for consumer-release signals across a cluster: what the waiter consumes after it (TMEM accumulators already drained with
+// tcgen05.wait::ld, shared memory filled by TMA) is not this thread's generic-proxy data.  The `.release.cluster` form
+// compiles to MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR in front of every arrive (SASS) — ~1 us on the issuing thread; with it
+// on the MMA thread the 2-CTA A-score kernel ran at 20.9 ms instead of 9.5 (measured).  -DLOVR_REMOTE_ARRIVE_RELEASE_CLUSTER=1
+// restores it (A/B timing).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+#if defined(LOVR_REMOTE_ARRIVE_RELEASE_CLUSTER)
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+#else
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+#endif
 }
 // TMA load whose completion bytes are credited to an mbarrier that may live in the PEER CTA (cluster address).
 __device__ __forceinline__ void tma_load_3d_2sm(void* smem_dst, const CUtensorMap* m, uint32_t mbar_cluster_addr, int c0,
