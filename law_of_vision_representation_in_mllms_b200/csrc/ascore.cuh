@@ -22,7 +22,6 @@
 // whole tile ahead of the MMA issuer).
 #pragma once
 #include "gemm.cuh"
-#include "gemm2.cuh"
 #include "scores.cuh"
 
 namespace lovr {
@@ -34,9 +33,6 @@ struct AScoreArgs {
   int x, y, K, n_pairs;
   const float* inv_ref;  // [n_pairs, y] 1 / ||ref|| with the reference's epsilons (rownorm_inv_bf16_kernel)
   int prefetch;          // k-blocks of L2 prefetch ahead of the TMA loads (0 = off, the default: see AScoreSmem)
-  int rotate;            // 1: the m tiles of a pair walk the `ref` tiles in rotated order (tile i of m tile mt is n tile
-                         // (i + mt) % n_tiles), so the CTAs working on one pair first-touch DIFFERENT `ref` tiles and find
-                         // the others in L2 instead of all waiting on the same HBM miss; the row maximum is order-free
   float* rowmax;         // [n_pairs, x]
 };
 
@@ -137,17 +133,15 @@ ascore_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         if (p.prefetch > 0 && pf.u < units) {
           const int pb = pf.u / m_tiles, pmt = pf.u % m_tiles;
           if (pf.nt == 0) tma_prefetch_3d(&tmA, pf.kb * kBK, pmt * kBM, pb);
-          if (pmt == 0 || pf.u < static_cast<int>(gridDim.x))
-            tma_prefetch_3d(&tmB, pf.kb * kBK, (p.rotate ? (pf.nt + pmt) % n_tiles : pf.nt) * BN, pb);
+          if (pmt == 0 || pf.u < static_cast<int>(gridDim.x)) tma_prefetch_3d(&tmB, pf.kb * kBK, pf.nt * BN, pb);
           advance(pf);
         }
         const int b = cur.u / m_tiles, mt = cur.u % m_tiles;
-        const int nt = p.rotate ? (cur.nt + mt) % n_tiles : cur.nt;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = stage_base + stage * L::kStageBytes;
         mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
         tma_load_3d(sa, &tmA, &full_bar[stage], cur.kb * kBK, mt * kBM, b);
-        tma_load_3d(sa + L::kABytes, &tmB, &full_bar[stage], cur.kb * kBK, nt * BN, b);
+        tma_load_3d(sa + L::kABytes, &tmB, &full_bar[stage], cur.kb * kBK, cur.nt * BN, b);
         if (++stage == kAsStages) { stage = 0; phase ^= 1; }
       }
     }
@@ -193,14 +187,13 @@ ascore_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const float* cs = p.inv_ref + static_cast<size_t>(b) * p.y;
       float run_max = -INFINITY;
       float rs = 0.f;
-      for (int i = 0; i < n_tiles; ++i) {
-        const int nt = p.rotate ? (i + mt) % n_tiles : i;
+      for (int nt = 0; nt < n_tiles; ++nt) {
         mbar_wait(&tmem_full[acc], acc_phase);
         mbar_wait(&aux_full[acc], acc_phase);
         tc_fence_after();
         // this unit's row scale was published with its first tile; taken into a register now, while the accumulator
         // hand-shake still keeps the norm warps from reusing the slot
-        if (i == 0) rs = inv_other[(k & 1) * kBM + rt];
+        if (nt == 0) rs = inv_other[(k & 1) * kBM + rt];
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
@@ -252,217 +245,6 @@ ascore_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------------------------
-// 2-CTA variant (tcgen05 cta_group::2).  The 1-CTA kernel above stops at ~56 % tensor-pipe activity because every 128 x BN x 64
-// step pulls 16 KB of `other` AND all BN rows of `ref` into ONE SM: 77 FLOP per shared-memory byte filled, ~70 GB/s per SM of
-// L2 -> SM traffic — the same per-SM fill rate at which the 1-CTA dense GEMM saturates (profiles/r02_ncu_summary.md).  Here a
-// cluster of two CTAs takes a 256-row tile of `other` (128 rows each) and each CTA loads HALF of the `ref` tile; the pair's
-// tensor cores read both halves (UMMA_M = 256): 28 KB instead of 40 KB per step and SM at BN = 192, 112 FLOP per byte.
-//   unit            (pair b, 256-row tile m2 of `other`), dealt round-robin to the clusters
-//   full[s]         leader only; armed with both CTAs' bytes, every TMA load of either CTA signals it (as in gemm2.cuh)
-//   a_ready[s]      both CTAs, count 1: the leader's MMA thread forwards "stage s has landed" (local + remote arrive) to the
-//                   norm warps — the peer's loads complete on the LEADER's barrier, so the peer has no local signal of its own
-//   empty[s]        both CTAs, count 1 + 4: multicast tcgen05.commit + the four local norm warps
-//   tmem_full[acc]  both CTAs (multicast commit); tmem_empty[acc] leader only, count 8 (epilogue warps of both CTAs)
-//   aux_full[acc]   local, count 4: norm warps -> epilogue, as above
-// The norm warps trail the MMA issuer (a_ready), the issuer waits for tmem_empty before each tile, so neither aux_full nor the
-// inv_other slots can be lapped; no K/64 > stages condition here.
-template <int BN>
-struct AScore2Smem {
-  static constexpr int kABytes = kBM * kBK * 2;
-  static constexpr int kBBytes = (BN / 2) * kBK * 2;  // this CTA's half of the ref tile
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 6 : (BN == 192) ? 7 : 8;
-  static constexpr int kTotal = kStages * kStageBytes + 2 * kBM * 4 /*inv_other*/ + 512 /*barriers*/ + 1024 /*align*/;
-};
-
-template <int BN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kAsThreads, 1)
-ascore2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const AScoreArgs p) {
-  using L = AScore2Smem<BN>;
-  constexpr uint32_t kTmemCols = (2 * BN <= 256) ? 256 : 512;
-  constexpr uint32_t kIdesc = make_idesc_16(256, BN, 0, 0, false);  // UMMA_M = 256 across the CTA pair
-  constexpr int kSt = L::kStages;
-
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int m_tiles = (p.x + 255) / 256;
-  const int n_tiles = (p.y + BN - 1) / BN;
-  const int k_blocks = p.K / kBK;
-  const int units = p.n_pairs * m_tiles;
-  uint8_t* stage_base = smem;
-  float* inv_other = reinterpret_cast<float*>(smem + kSt * L::kStageBytes);  // [2][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(inv_other + 2 * kBM);
-  uint64_t* full_bar = bars;               // [kSt]  (used in the leader)
-  uint64_t* empty_bar = bars + kSt;        // [kSt]
-  uint64_t* a_ready = bars + 2 * kSt;      // [kSt]
-  uint64_t* tmem_full = bars + 3 * kSt;    // [2]
-  uint64_t* tmem_empty = tmem_full + 2;    // [2]    (used in the leader)
-  uint64_t* aux_full = tmem_empty + 2;     // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_full + 2);
-
-  const int warp = uniform_warp_index(), lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const int cluster = blockIdx.x >> 1;
-  const int num_clusters = gridDim.x >> 1;
-
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-    for (int i = 0; i < kSt; ++i) {
-      mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1 + 4);
-      mbar_init(&a_ready[i], 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 8);
-      mbar_init(&aux_full[i], 4);
-    }
-    fence_barrier_init();
-  }
-  cluster_sync_all();  // both CTAs' barriers exist before any remote signal
-  if (warp == 1) {
-    tmem_alloc_2sm(tmem_slot, kTmemCols);
-    tmem_relinquish_2sm();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = warp_uniform(*tmem_slot);
-
-  if (warp == 0) {
-    // ===================================================================== TMA producer (both CTAs)
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int u = cluster; u < units; u += num_clusters) {
-        const int b = u / m_tiles, m2 = u % m_tiles;
-        const int arow = m2 * 256 + static_cast<int>(rank) * kBM;
-        for (int i = 0; i < n_tiles; ++i) {
-          const int nt = p.rotate ? (i + m2) % n_tiles : i;
-          const int brow = nt * BN + static_cast<int>(rank) * (BN / 2);
-          for (int kb = 0; kb < k_blocks; ++kb) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* sa = stage_base + stage * L::kStageBytes;
-            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
-            const uint32_t leader_full = mapa_shared(smem_u32(&full_bar[stage]), 0);
-            tma_load_3d_2sm(sa, &tmA, leader_full, kb * kBK, arow, b);
-            tma_load_3d_2sm(sa + L::kABytes, &tmB, leader_full, kb * kBK, brow, b);
-            if (++stage == kSt) { stage = 0; phase ^= 1; }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================================================================== MMA issuer (leader CTA only)
-    if (rank == 0) {
-      constexpr uint32_t kDescHi = smem_desc_hi_sw128(1024);
-      const uint32_t a_lo0 = smem_desc_lo(smem_u32(stage_base), 16);
-      const uint32_t b_lo0 = smem_desc_lo(smem_u32(stage_base) + L::kABytes, 16);
-      const uint32_t peer_ready0 = mapa_shared(smem_u32(&a_ready[0]), 1);
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      for (int u = cluster; u < units; u += num_clusters)
-        for (int t = 0; t < n_tiles; ++t) {
-          mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + acc * BN;
-          for (int kb = 0; kb < k_blocks; ++kb) {
-            mbar_wait(&full_bar[stage], phase);
-            tc_fence_after();
-            if (lane == 0) {
-              mbar_arrive(&a_ready[stage]);
-              mbar_arrive_cluster(peer_ready0 + stage * 8);
-              const uint32_t a_lo = a_lo0 + stage * (L::kStageBytes >> 4);
-              const uint32_t b_lo = b_lo0 + stage * (L::kStageBytes >> 4);
-#pragma unroll
-              for (int k = 0; k < kBK / 16; ++k)
-                umma_bf16_ss_2sm(d_tmem, smem_desc_join(kDescHi, a_lo + 2 * k), smem_desc_join(kDescHi, b_lo + 2 * k), kIdesc,
-                                 (kb | k) != 0 ? 1u : 0u);
-              umma_commit_2sm(&empty_bar[stage]);
-              if (kb == k_blocks - 1) umma_commit_2sm(&tmem_full[acc]);
-            }
-            __syncwarp();
-            if (++stage == kSt) { stage = 0; phase ^= 1; }
-          }
-          acc ^= 1;
-          if (acc == 0) acc_phase ^= 1;
-        }
-    }
-  } else if (warp < 6) {
-    // ===================================================================== epilogue: running row maximum (both CTAs)
-    const int quarter = warp & 3;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    int k = 0;
-    const int rt = quarter * 32 + lane;
-    const uint32_t leader_empty0 = mapa_shared(smem_u32(&tmem_empty[0]), 0);
-    for (int u = cluster; u < units; u += num_clusters, ++k) {
-      const int b = u / m_tiles, m2 = u % m_tiles;
-      const float* cs = p.inv_ref + static_cast<size_t>(b) * p.y;
-      float run_max = -INFINITY;
-      float rs = 0.f;
-      for (int i = 0; i < n_tiles; ++i) {
-        const int nt = p.rotate ? (i + m2) % n_tiles : i;
-        mbar_wait(&tmem_full[acc], acc_phase);
-        mbar_wait(&aux_full[acc], acc_phase);
-        tc_fence_after();
-        if (i == 0) rs = inv_other[(k & 1) * kBM + rt];
-        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          const int col0 = nt * BN + c * 32;
-          if (col0 >= p.y) break;  // warp-uniform
-          uint32_t r0[32];
-          tmem_ld_32x32b_x32(t_row + c * 32, r0);
-          tmem_ld_wait();
-#pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const float v = __uint_as_float(r0[e]) * __ldg(cs + min(col0 + e, p.y - 1));  // same address in every lane
-            if (col0 + e < p.y) run_max = fmaxf(run_max, v);
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(leader_empty0 + acc * 8);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
-      }
-      const int row = m2 * 256 + static_cast<int>(rank) * kBM + rt;
-      if (row < p.x) p.rowmax[static_cast<size_t>(b) * p.x + row] = run_max * rs;
-    }
-  } else {
-    // ===================================================================== norm warps (both CTAs, own 128 rows)
-    const int t = threadIdx.x - 6 * 32;  // 0..127: tile row
-    int stage = 0, acc = 0;
-    uint32_t phase = 0;
-    int k = 0;
-    for (int u = cluster; u < units; u += num_clusters, ++k)
-      for (int nt = 0; nt < n_tiles; ++nt) {
-        float ss = 0.f;
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&a_ready[stage], phase);
-          if (nt == 0) ss += row_sumsq_128B(smem_u32(stage_base + stage * L::kStageBytes) + t * 128, t);
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&empty_bar[stage]);
-          if (++stage == kSt) { stage = 0; phase ^= 1; }
-        }
-        if (nt == 0) inv_other[(k & 1) * kBM + t] = inv_norm_scale(ss);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&aux_full[acc]);
-        acc ^= 1;
-      }
-  }
-
-  tc_fence_before();
-  cluster_sync_all();  // nobody exits (or frees TMEM) while the peer may still signal or read this CTA
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc_2sm(tmem_base, kTmemCols);
   }
 }
 

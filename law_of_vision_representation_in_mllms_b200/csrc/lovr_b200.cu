@@ -923,43 +923,6 @@ int lovr_a_score_maxcos(const void* other, const void* ref, int32_t dtype, int64
   // bf16 features: the `other` norms come out of the shared-memory tiles of the GEMM itself (ascore.cuh), so `other` is read
   // from HBM once; only `ref` gets a norm pre-pass.  Needs more k-blocks than pipeline stages (its barrier-phase argument).
   static const int fuse_env = [] { const char* e = getenv("LOVR_A_SCORE_FUSED"); return e ? atoi(e) : 1; }();
-  // 2-CTA form of the same kernel (each SM loads half of the `ref` tile): LOVR_A_SCORE_2CTA=0 selects the 1-CTA kernel (A/B)
-  // It runs a 128 x BN tile 14 % faster (7.9 vs 9.2 us at BN = 192, K = 1024) but pads x to 256 rows: the default takes it only
-  // when that costs nothing (x = 576: 768 vs 640 padded rows — measured 9.57 vs 9.30 ms at C3, so the 1-CTA kernel stays).
-  // LOVR_A_SCORE_2CTA=1 / 0 force either form (read per call so one test process can run both).
-  const char* two_cta_s = getenv("LOVR_A_SCORE_2CTA");
-  const int two_cta_env = two_cta_s ? atoi(two_cta_s) : ((x + 255) / 256 * 256 == (x + 127) / 128 * 128);
-  const char* rotate_s = getenv("LOVR_A_ROTATE");
-  const int rotate = rotate_s ? atoi(rotate_s) : 1;
-  if (dtype == LOVR_DT_BF16 && fuse_env && two_cta_env && device_info().sms >= 2) {
-    rownorm_inv_bf16_kernel<<<static_cast<unsigned>((rows_r + wpb - 1) / wpb), wpb * 32, 0, s>>>(
-        static_cast<const __nv_bfloat16*>(ref), inv_r, rows_r, D);
-    LAUNCH_CHECK("rownorm_inv_bf16_kernel");
-    const size_t smem = bn == 128 ? AScore2Smem<128>::kTotal : bn == 192 ? AScore2Smem<192>::kTotal : AScore2Smem<256>::kTotal;
-    const void* kern = bn == 128   ? reinterpret_cast<const void*>(ascore2_tcgen05_kernel<128>)
-                       : bn == 192 ? reinterpret_cast<const void*>(ascore2_tcgen05_kernel<192>)
-                                   : reinterpret_cast<const void*>(ascore2_tcgen05_kernel<256>);
-    CUtensorMap ta, tb;
-    int rc;
-    if ((rc = make_tmap(&ta, other, 2, D, x, n_pairs, D, static_cast<uint64_t>(D) * x, 64, kBM))) return rc;
-    if ((rc = make_tmap(&tb, ref, 2, D, y, n_pairs, D, static_cast<uint64_t>(D) * y, 64, bn / 2))) return rc;
-    if ((rc = ensure_smem(kern, smem))) return rc;
-    AScoreArgs a{};
-    a.x = x; a.y = y; a.K = D; a.n_pairs = static_cast<int>(n_pairs); a.inv_ref = inv_r; a.rowmax = rowmax; a.rotate = rotate;
-    const long long units = static_cast<long long>(n_pairs) * ((x + 255) / 256);
-    const int max_clusters = device_info().sms / 2;
-    const int grid = 2 * (units < max_clusters ? static_cast<int>(units) : max_clusters);
-    {
-      ProfScope prof_scope(s, LOVR_PROF_OTHER, 2.0 * x * static_cast<double>(y) * D * n_pairs);
-      if (bn == 128) ascore2_tcgen05_kernel<128><<<grid, kAsThreads, smem, s>>>(ta, tb, a);
-      else if (bn == 192) ascore2_tcgen05_kernel<192><<<grid, kAsThreads, smem, s>>>(ta, tb, a);
-      else ascore2_tcgen05_kernel<256><<<grid, kAsThreads, smem, s>>>(ta, tb, a);
-    }
-    LAUNCH_CHECK("ascore2_tcgen05_kernel");
-    pair_mean_kernel<<<static_cast<unsigned>(n_pairs), 256, 0, s>>>(rowmax, pair_score, x);
-    LAUNCH_CHECK("pair_mean_kernel");
-    return 0;
-  }
   if (dtype == LOVR_DT_BF16 && fuse_env && D / kBK > 5) {
     rownorm_inv_bf16_kernel<<<static_cast<unsigned>((rows_r + wpb - 1) / wpb), wpb * 32, 0, s>>>(
         static_cast<const __nv_bfloat16*>(ref), inv_r, rows_r, D);
@@ -981,7 +944,7 @@ int lovr_a_score_maxcos(const void* other, const void* ref, int32_t dtype, int64
     if ((rc = make_tmap(&tb, ref, 2, D, y, n_pairs, D, static_cast<uint64_t>(D) * y, 64, bn))) return rc;
     if ((rc = ensure_smem(kern, smem))) return rc;
     AScoreArgs a{};
-    a.x = x; a.y = y; a.K = D; a.n_pairs = static_cast<int>(n_pairs); a.inv_ref = inv_r; a.rowmax = rowmax; a.rotate = rotate;
+    a.x = x; a.y = y; a.K = D; a.n_pairs = static_cast<int>(n_pairs); a.inv_ref = inv_r; a.rowmax = rowmax;
     { const char* e = getenv("LOVR_A_PREFETCH"); a.prefetch = e ? atoi(e) : 0; }
     const long long units = static_cast<long long>(n_pairs) * ((x + kBM - 1) / kBM);
     const int grid = units < device_info().sms ? static_cast<int>(units) : device_info().sms;

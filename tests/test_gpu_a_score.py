@@ -65,12 +65,9 @@ def test_folder_driver_mirrors_compute_py(tmp_path, a_gold):
 
 @pytest.mark.parametrize("n,x,y,D", [(3, 576, 576, 1024), (3, 576, 256, 1024), (2, 256, 576, 4096), (5, 130, 700, 512),
                                      (4, 1, 1, 320), (3, 577, 129, 384), (2, 100, 1500, 1024)])
-@pytest.mark.parametrize("two_cta", ["1", "0"])
-def test_a_pairs_bf16_single_pass_kernel(n, x, y, D, two_cta, monkeypatch):
-    """bf16 features take the one-pass kernel (norms from the GEMM's own shared-memory tiles, ascore.cuh), in its 2-CTA form
-    (default) and its 1-CTA form (LOVR_A_SCORE_2CTA=0; D > 320 only, else the two-pass path): ragged tiles on both sides,
-    every BN instance (y = 576 -> 192, 256 -> 128/256, 700 -> 128 ...), zero rows, tiles whose second CTA is all padding."""
-    monkeypatch.setenv("LOVR_A_SCORE_2CTA", two_cta)
+def test_a_pairs_bf16_single_pass_kernel(n, x, y, D):
+    """bf16 features with D > 256 take the one-pass kernel (norms from the GEMM's own shared-memory tiles, ascore.cuh):
+    ragged tiles on both sides, every BN instance (y = 576 -> 192, 256 -> 128/256, 700 -> 128 ...), zero rows."""
     g = torch.Generator().manual_seed(n * 1000 + x + y)
     o = (torch.randn(n, x, D, generator=g) * (0.2 + torch.rand(n, x, 1, generator=g))).bfloat16()
     r = (torch.randn(n, y, D, generator=g) + 0.3 * torch.randn(n, 1, D, generator=g)).bfloat16()
@@ -81,13 +78,11 @@ def test_a_pairs_bf16_single_pass_kernel(n, x, y, D, two_cta, monkeypatch):
     assert (got.double() - want.double()).abs().max() < TOL
 
 
-@pytest.mark.parametrize("two_cta", ["1", "0"])
-def test_a_pairs_bf16_single_pass_many_pairs_persistent_loop(two_cta, monkeypatch):
+def test_a_pairs_bf16_single_pass_many_pairs_persistent_loop():
     """More pairs than SMs: every CTA walks several pairs (scale buffers alternate by pair parity); bitwise repeatable and
     independent of how the pairs are batched."""
-    monkeypatch.setenv("LOVR_A_SCORE_2CTA", two_cta)
     g = torch.Generator().manual_seed(77)
-    n, x, y, D = 700, 150, 200, 384
+    n, x, y, D = 700, 150, 200, 320
     o = torch.randn(n, x, D, generator=g).bfloat16().cuda()
     r = (0.5 * o[:, :1].float().cpu() + torch.randn(n, y, D, generator=g)).bfloat16().cuda()
     a1, a2 = A.a_score_pairs(o, r), A.a_score_pairs(o, r)
