@@ -26,8 +26,17 @@
 namespace lovr {
 
 constexpr int kKpN = 32;
-constexpr int kKpStages = 6;
-constexpr int kKpTilesPerUnit = 4;
+#ifndef LOVR_KP_STAGES
+#define LOVR_KP_STAGES 6
+#endif
+#ifndef LOVR_KP_TILES_PER_UNIT
+#define LOVR_KP_TILES_PER_UNIT 8
+#endif
+// -DLOVR_KP_STAGES / -DLOVR_KP_TILES_PER_UNIT: A/B builds (build.py --out).  Measured at 512 P=60 pairs (us per pair): tiles per
+// unit 4 / 8 / 10 / 15 / 29 = 1.58 / 1.46 / 1.44 / 1.43 / 1.48 (each unit re-gathers the pair's K source rows; 8 keeps ~7 waves of
+// units at the 256-pair chunks the job uses); stages 6 / 8 / 9 = 1.58 / 1.57 / 1.57 (6 keeps D = 2048 inside 227 KB).
+constexpr int kKpStages = LOVR_KP_STAGES;
+constexpr int kKpTilesPerUnit = LOVR_KP_TILES_PER_UNIT;
 constexpr int kKpThreads = 64 + 4 * 32 + 4 * 32;
 constexpr int kKpABytes = kBM * kBK * 2;
 
