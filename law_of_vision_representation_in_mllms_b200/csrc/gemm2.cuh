@@ -123,9 +123,12 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const int pair = blockIdx.x >> 1;
   const int num_pairs = gridDim.x >> 1;
 
+  // units: (batch b, 256-row tile mt, 256-column tile nt), nt fastest.  Dense layers: batch 1, N a multiple of 256.  Batched
+  // similarity GEMMs (C score): one problem per pair through the third tensor-map coordinate; rows / columns past M / N are
+  // zero-filled on load and clipped on store.
   const int m_tiles = (p.M + 255) / 256;
-  const int n_tiles = p.N / BN;
-  const int units = m_tiles * n_tiles;
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const int units = (p.batch > 0 ? p.batch : 1) * m_tiles * n_tiles;
   const int k_blocks = p.K / kBK;
 
   if (threadIdx.x == 0) {
@@ -160,15 +163,16 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       uint32_t phase = 0;
       for (int unit = pair; unit < units; unit += num_pairs) {
         const int nt = unit % n_tiles;
-        const int mt = unit / n_tiles;
+        const int mt = (unit / n_tiles) % m_tiles;
+        const int b = unit / (n_tiles * m_tiles);
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = stage_base + stage * L::kStageBytes;
           uint8_t* sb = sa + L::kABytes;
           if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
           const uint32_t leader_full = mapa_shared(smem_u32(&full_bar[stage]), 0);
-          tma_load_3d_2sm(sa, &tmA, leader_full, kb * kBK, mt * 256 + static_cast<int>(rank) * 128, 0);
-          tma_load_3d_2sm(sb, &tmB, leader_full, kb * kBK, nt * BN + static_cast<int>(rank) * 128, 0);
+          tma_load_3d_2sm(sa, &tmA, leader_full, kb * kBK, mt * 256 + static_cast<int>(rank) * 128, b);
+          tma_load_3d_2sm(sb, &tmB, leader_full, kb * kBK, nt * BN + static_cast<int>(rank) * 128, b);
           if (++stage == kStages2) { stage = 0; phase ^= 1; }
         }
       }
@@ -221,14 +225,15 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     float run_max = 0.f;
     for (int unit = pair; unit < units; unit += num_pairs) {
       const int nt = unit % n_tiles;
-      const int mt = unit / n_tiles;
+      const int mt = (unit / n_tiles) % m_tiles;
+      const int b = unit / (n_tiles * m_tiles);
       const int row0 = mt * 256 + static_cast<int>(rank) * 128 + quarter * 32;
       float rs = 1.0f, rm = 0.0f;  // folded LayerNorm: the row's statistics are merged while the tile's MMAs still run
       if constexpr (EPI == EPI_BF16) ln_row_scales(p, min(row0 + lane, p.M - 1), rs, rm);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-      epilogue_tile<CW, EPI, ACT, F16, RB>(t_row + chalf * CW, nt * BN + chalf * CW, row0, 0, p, tmC, my_stage, my_rbar, lane,
+      epilogue_tile<CW, EPI, ACT, F16, RB>(t_row + chalf * CW, nt * BN + chalf * CW, row0, b, p, tmC, my_stage, my_rbar, lane,
                                           row_sw, g, run_max, rs, rm);
       tc_fence_before();
       __syncwarp();

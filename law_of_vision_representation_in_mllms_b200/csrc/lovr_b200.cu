@@ -250,11 +250,12 @@ int launch_gemm2_inst(const CUtensorMap& a, const CUtensorMap& b, const CUtensor
   auto kern = lovr::gemm2_tcgen05_kernel<EPI, ACT, F16, EW>;
   const int smem = lovr::Gemm2Smem<EPI, EW>::kTotal;
   if (int rc = ensure_smem(reinterpret_cast<const void*>(kern), smem)) return rc;
-  const int units = ((args.M + 255) / 256) * (args.N / 256);
+  const long long units_ll = static_cast<long long>(args.batch > 0 ? args.batch : 1) * ((args.M + 255) / 256) * ((args.N + 255) / 256);
+  const int units = units_ll > 0x3fffffff ? 0x3fffffff : static_cast<int>(units_ll);
   int grid = 2 * units < device_info().sms ? 2 * units : (device_info().sms & ~1);
   if (grid <= 0) return 0;
   size_t pidx = 0;
-  const bool profiled = prof_begin(s, 2.0 * args.M * args.N * static_cast<double>(args.K), &pidx);
+  const bool profiled = prof_begin(s, 2.0 * args.M * args.N * static_cast<double>(args.K) * (args.batch > 0 ? args.batch : 1), &pidx);
   kern<<<grid, lovr::Gemm2Smem<EPI, EW>::kThreads, smem, s>>>(a, b, c, args);  // __cluster_dims__(2,1,1) on the kernel
   if (profiled) prof_end(s, pidx);
   LAUNCH_CHECK("gemm2_tcgen05_kernel");
@@ -1076,11 +1077,16 @@ int c_dense_similarity(const void* desc1, const void* desc2, int32_t dtype, int6
   CUtensorMap ta, tb, tc;
   int rc;
   if ((rc = make_tmap(&ta, a_ptr, 2, K, PP, n_pairs, K, static_cast<uint64_t>(K) * PP, 64, kBM))) return rc;
-  if ((rc = make_tmap(&tb, b_ptr, 2, K, PP, n_pairs, K, static_cast<uint64_t>(K) * PP, 64, 256))) return rc;
+  // CTA-pair kernel (each SM loads half of the desc2 tile; the 1-CTA 128 x 256 tile is bound by shared-memory bandwidth at
+  // ~67 % of the tensor pipe) when a pair has more than one 128-row tile; LOVR_CSIM_2CTA=0 keeps the 1-CTA kernel (A/B)
+  const char* pairs_s = getenv("LOVR_CSIM_2CTA");
+  const bool pairs = (pairs_s ? atoi(pairs_s) != 0 : true) && gemm_use_pairs() != 0 && PP > 128;
+  if ((rc = make_tmap(&tb, b_ptr, 2, K, PP, n_pairs, K, static_cast<uint64_t>(K) * PP, 64, pairs ? 128 : 256))) return rc;
   if ((rc = make_tmap(&tc, sim, 4, PP, PP, n_pairs, l.sim_ld, static_cast<uint64_t>(l.sim_ld) * PP, 32, 32))) return rc;
   GemmArgs g{};
   g.M = PP; g.N = PP; g.K = K; g.batch = static_cast<int>(n_pairs); g.n_inner = 1;
   g.bias = nullptr; g.colscale = inv2; g.rowscale = inv1; g.rowmax = nullptr; g.n_valid = PP; g.scale_ld = l.scale_ld;
+  if (pairs) return launch_gemm2(EPI_F32, ACT_NONE, false, ta, tb, tc, g, s);
   return launch_gemm(256, EPI_F32, ACT_NONE, false, ta, tb, tc, g, s);
 }
 struct MnnLayout {

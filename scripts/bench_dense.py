@@ -14,5 +14,5 @@ for _ in range(3):
     CS.get_flow(d1, d2)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 3
-print("LOVR_C_ARGMAX_FUSED", os.environ.get("LOVR_C_ARGMAX_FUSED", "1"), "dense flow us per pair", 1e3 * ms / n,
+print("LOVR_CSIM_2CTA", os.environ.get("LOVR_CSIM_2CTA", "1"), "dense flow us per pair", 1e3 * ms / n,
       "TFLOP/s", 2.0 * P ** 4 * 1024 * n / ms / 1e9)
